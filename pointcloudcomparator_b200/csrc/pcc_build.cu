@@ -1,0 +1,388 @@
+// pcc_build.cu -- index lifetime, uniform-grid build (cell keys -> counting sort -> cell-start scan) and
+// query-batch preparation (cell keys -> radix sort) for libpcc_search.so.
+//
+// Replaces pcl::search::KdTree::setInputCloud -> KdTreeFLANN::setInputCloud -> flann::KDTreeSingleIndex::buildIndex
+// (reference call sites: src/segmentation.cpp:122 and implicitly every consumer).
+#include <cub/cub.cuh>
+#include <stdarg.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+#include "pcc_internal.h"
+
+namespace pcc {
+
+thread_local std::string g_error;
+int64_t g_launches = 0;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+static constexpr int kMaxDim = 2048;                 // covered_d2()'s rounding margin assumes this cap
+static constexpr int64_t kMaxCellsDefault = 1ll << 28;
+
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
+static inline float ord2f(int i) { int j = i >= 0 ? i : i ^ 0x7FFFFFFF; float f; memcpy(&f, &j, 4); return f; }
+
+// raw strided rows -> float4 (x, y, z, original row as int bits; NaN w marks a skipped row) + bbox + finite count
+__global__ void extract_kernel(const uint8_t *__restrict__ raw, int stride, const int32_t *__restrict__ indices, int64_t m,
+                               int64_t n_rows, float4 *__restrict__ stage, int *__restrict__ bbox, unsigned long long *__restrict__ n_finite) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+    int fin = 0;
+    if (i < m) {
+        int64_t row = indices ? (int64_t)indices[i] : i;
+        float x = CUDART_NAN_F, y = x, z = x;
+        if (row >= 0 && row < n_rows) {
+            const float *p = (const float *)(raw + row * (int64_t)stride);
+            x = p[0]; y = p[1]; z = p[2];
+        }
+        fin = finite3(x, y, z);
+        stage[i] = make_float4(x, y, z, fin ? __int_as_float((int)row) : CUDART_NAN_F);
+        if (fin) { lo[0] = hi[0] = f2ord(x); lo[1] = hi[1] = f2ord(y); lo[2] = hi[2] = f2ord(z); }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { lo[d] = __reduce_min_sync(0xffffffffu, lo[d]); hi[d] = __reduce_max_sync(0xffffffffu, hi[d]); }
+    unsigned nf = __reduce_add_sync(0xffffffffu, (unsigned)fin);
+    if ((threadIdx.x & 31) == 0 && nf) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { atomicMin(bbox + d, lo[d]); atomicMax(bbox + 3 + d, hi[d]); }
+        atomicAdd(n_finite, (unsigned long long)nf);
+    }
+}
+
+struct BinParams { float ox, oy, oz, inv; int nx, ny, nz; };
+__device__ __forceinline__ uint32_t cell_of(const BinParams &b, float x, float y, float z) {
+    int cx = grid_c(grid_u(x, b.ox, b.inv), b.nx), cy = grid_c(grid_u(y, b.oy, b.inv), b.ny), cz = grid_c(grid_u(z, b.oz, b.inv), b.nz);
+    return (uint32_t)(((size_t)cz * b.ny + cy) * b.nx + cx);
+}
+// counting sort pass 1: per-cell histogram; the atomic's return value is the point's rank inside its cell
+__global__ void bin_kernel(const float4 *__restrict__ stage, int64_t m, BinParams b, uint32_t *__restrict__ counts, uint2 *__restrict__ cellrank) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    float4 p = stage[i];
+    if (p.w != p.w) { if (cellrank) cellrank[i] = make_uint2(0xFFFFFFFFu, 0u); return; }
+    uint32_t c = cell_of(b, p.x, p.y, p.z);
+    uint32_t r = atomicAdd(counts + c, 1u);
+    if (cellrank) cellrank[i] = make_uint2(c, r);
+}
+__global__ void nonzero_kernel(const uint32_t *__restrict__ counts, int64_t n, unsigned long long *__restrict__ out) {
+    unsigned local = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) local += counts[i] != 0;
+    local = __reduce_add_sync(0xffffffffu, local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, (unsigned long long)local);
+}
+// counting sort pass 2: scatter to cell_start[cell] + rank
+__global__ void scatter_kernel(const float4 *__restrict__ stage, const uint2 *__restrict__ cellrank, int64_t m,
+                               const uint32_t *__restrict__ cell_start, float4 *__restrict__ pts) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    uint2 cr = cellrank[i];
+    if (cr.x == 0xFFFFFFFFu) return;
+    pts[cell_start[cr.x] + cr.y] = stage[i];
+}
+// inv_pos[original row] = position in the sorted array (0xFFFFFFFF for rows that are not indexed)
+__global__ void inverse_kernel(const float4 *__restrict__ pts, int64_t n, uint32_t *__restrict__ inv_pos) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) inv_pos[__float_as_int(pts[i].w)] = (uint32_t)i;
+}
+int rebuild_inverse(pcc_index *idx, cudaStream_t s) {
+    PCC_TRY(idx->inv_pos.reserve((size_t)std::max<int64_t>(idx->n_input, 1) * 4));
+    PCC_CUDA(cudaMemsetAsync(idx->inv_pos.p, 0xFF, (size_t)std::max<int64_t>(idx->n_input, 1) * 4, s));
+    if (idx->n_indexed > 0) {
+        inverse_kernel<<<(unsigned)((idx->n_indexed + 255) / 256), 256, 0, s>>>(idx->pts.as<float4>(), idx->n_indexed, idx->inv_pos.as<uint32_t>());
+        PCC_LAUNCHED();
+        PCC_CUDA(cudaGetLastError());
+    }
+    idx->inv_valid = true;
+    return PCC_OK;
+}
+
+// query rows -> float4 + cell key (n_cells for non-finite rows so they sort last) + identity permutation
+__global__ void qprep_kernel(const uint8_t *__restrict__ raw, int stride, int64_t nq, BinParams b, uint32_t bad_key,
+                             float4 *__restrict__ qbuf, uint32_t *__restrict__ keys, uint32_t *__restrict__ perm) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const float *p = (const float *)(raw + i * (int64_t)stride);
+    float x = p[0], y = p[1], z = p[2];
+    qbuf[i] = make_float4(x, y, z, 0.f);
+    if (keys) { keys[i] = finite3(x, y, z) ? cell_of(b, x, y, z) : bad_key; perm[i] = (uint32_t)i; }
+}
+
+static inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)std::max<int64_t>(1, (n + threads - 1) / threads); }
+
+static double occupancy_target(int k_hint) {
+    const char *e = getenv("PCC_OCC");
+    if (e && atof(e) > 0) return atof(e);
+    int k = k_hint > 0 ? k_hint : 16;
+    return std::max(1.0, 0.35 * k);
+}
+
+static void dims_for(const double ext[3], double cell, int dims[3]) {
+    for (int d = 0; d < 3; ++d) dims[d] = (int)std::min<double>(kMaxDim, std::floor(ext[d] / cell) + 1);
+}
+static double clamp_cell(const double ext[3], double cell, int64_t max_cells) {
+    double mx = std::max(ext[0], std::max(ext[1], ext[2]));
+    if (!(cell > 0) || !std::isfinite(cell)) cell = mx > 0 ? mx : 1.0;
+    cell = std::max(cell, mx / (kMaxDim - 1));
+    for (int it = 0; it < 64; ++it) {
+        int d[3]; dims_for(ext, cell, d);
+        double total = (double)d[0] * d[1] * d[2];
+        if (total <= (double)max_cells) break;
+        cell *= std::max(1.02, std::cbrt(total / (double)max_cells));
+    }
+    return cell;
+}
+
+int prepare_queries(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int mem, cudaStream_t s, Queries *out) {
+    if (!idx->built) return fail(PCC_ERR_STATE, "index not built (call pcc_build first)");
+    if (q == nullptr) { out->self = true; out->nq = idx->n_indexed; out->rows = idx->n_input; out->q = nullptr; out->order = nullptr; return PCC_OK; }
+    if (nq < 0 || stride_bytes < 12 || (stride_bytes & 3)) return fail(PCC_ERR_INVALID, "bad query batch (nq=%lld stride=%d)", (long long)nq, stride_bytes);
+    out->self = false; out->nq = nq; out->rows = nq;
+    if (nq == 0) return PCC_OK;
+    const uint8_t *raw = (const uint8_t *)q;
+    if (mem == PCC_HOST) {
+        PCC_TRY(idx->raw.reserve((size_t)nq * stride_bytes));
+        PCC_CUDA(cudaMemcpyAsync(idx->raw.p, q, (size_t)nq * stride_bytes, cudaMemcpyHostToDevice, s));
+        raw = idx->raw.as<uint8_t>();
+    }
+    PCC_TRY(idx->qbuf.reserve((size_t)nq * sizeof(float4)));
+    const bool sort = nq > 2048;
+    BinParams b{idx->gh.ox, idx->gh.oy, idx->gh.oz, idx->gh.inv_cell, idx->gh.nx, idx->gh.ny, idx->gh.nz};
+    if (sort) {
+        PCC_TRY(idx->qkeys.reserve((size_t)nq * 4)); PCC_TRY(idx->qkeys2.reserve((size_t)nq * 4));
+        PCC_TRY(idx->qperm.reserve((size_t)nq * 4)); PCC_TRY(idx->qperm2.reserve((size_t)nq * 4));
+    }
+    qprep_kernel<<<blocks_for(nq, 256), 256, 0, s>>>(raw, stride_bytes, nq, b, (uint32_t)idx->gh.n_cells, idx->qbuf.as<float4>(),
+                                                     sort ? idx->qkeys.as<uint32_t>() : nullptr, sort ? idx->qperm.as<uint32_t>() : nullptr);
+    PCC_LAUNCHED();
+    PCC_CUDA(cudaGetLastError());
+    out->q = idx->qbuf.as<float4>();
+    out->order = nullptr;
+    if (sort) {
+        int bits = 1; while ((1ll << bits) <= idx->gh.n_cells && bits < 32) ++bits;
+        size_t tmp = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp, idx->qkeys.as<uint32_t>(), idx->qkeys2.as<uint32_t>(), idx->qperm.as<uint32_t>(), idx->qperm2.as<uint32_t>(), (int)nq, 0, bits, s);
+        PCC_TRY(idx->cub_tmp.reserve(tmp));
+        PCC_CUDA(cub::DeviceRadixSort::SortPairs(idx->cub_tmp.p, tmp, idx->qkeys.as<uint32_t>(), idx->qkeys2.as<uint32_t>(), idx->qperm.as<uint32_t>(), idx->qperm2.as<uint32_t>(), (int)nq, 0, bits, s));
+        g_launches += 4;
+        out->order = idx->qperm2.as<uint32_t>();
+    }
+    return PCC_OK;
+}
+
+int copy_out(void *dst, const void *src_dev, size_t bytes, int mem, cudaStream_t s) {
+    if (!bytes || dst == src_dev) return PCC_OK;
+    PCC_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, mem == PCC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
+    return PCC_OK;
+}
+
+}  // namespace pcc
+
+using namespace pcc;
+
+extern "C" {
+
+const char *pcc_last_error(void) { return g_error.c_str(); }
+int pcc_version(void) { return 100; }
+int64_t pcc_launch_count(void) { return g_launches; }
+
+int pcc_create(int device, pcc_index **out) {
+    if (!out) return fail(PCC_ERR_INVALID, "out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(PCC_ERR_CUDA, "no usable CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(PCC_ERR_INVALID, "device %d out of range (0..%d)", device, n - 1);
+    PCC_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PCC_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(PCC_ERR_CUDA, "device %d is sm_%d%d; libpcc_search is built for sm_100a only", device, prop.major, prop.minor);
+    pcc_index *idx = new pcc_index();
+    idx->device = device;
+    PCC_CUDA(cudaMallocHost(&idx->h_pinned, 4096));
+    PCC_CUDA(cudaEventCreate(&idx->ev0));
+    PCC_CUDA(cudaEventCreate(&idx->ev1));
+    *out = idx;
+    return PCC_OK;
+}
+
+void pcc_destroy(pcc_index *idx) {
+    if (!idx) return;
+    cudaSetDevice(idx->device);
+    Buf *bufs[] = {&idx->pts, &idx->cell_start, &idx->raw, &idx->stage4, &idx->cellrank, &idx->qbuf, &idx->qkeys, &idx->qkeys2, &idx->qperm, &idx->qperm2,
+                   &idx->cub_tmp, &idx->out_i, &idx->out_f, &idx->out_l, &idx->keys64, &idx->keys64b, &idx->misc, &idx->parent, &idx->inv_pos};
+    for (Buf *b : bufs) b->release();
+    if (idx->h_pinned) cudaFreeHost(idx->h_pinned);
+    if (idx->ev0) cudaEventDestroy(idx->ev0);
+    if (idx->ev1) cudaEventDestroy(idx->ev1);
+    delete idx;
+}
+
+int64_t pcc_size(const pcc_index *idx) { return idx ? idx->n_indexed : 0; }
+
+int pcc_grid_info(const pcc_index *idx, double out[5]) {
+    if (!idx || !idx->built) return fail(PCC_ERR_STATE, "index not built");
+    out[0] = idx->gh.nx; out[1] = idx->gh.ny; out[2] = idx->gh.nz; out[3] = idx->gh.cell; out[4] = idx->gh.occupancy;
+    return PCC_OK;
+}
+
+int pcc_set_timing(pcc_index *idx, int enable) { if (!idx) return fail(PCC_ERR_INVALID, "idx is NULL"); idx->timing = enable != 0; idx->last_ms = -1; return PCC_OK; }
+double pcc_last_kernel_ms(const pcc_index *idx) { return idx ? idx->last_ms : -1; }
+
+int pcc_build(pcc_index *idx, const void *pts, int64_t n, int stride_bytes, const int32_t *indices, int64_t n_idx,
+              float cell_hint, int k_hint, int mem, void *stream) {
+    if (!idx) return fail(PCC_ERR_INVALID, "idx is NULL");
+    if (n < 0 || (n > 0 && !pts) || stride_bytes < 12 || (stride_bytes & 3)) return fail(PCC_ERR_INVALID, "bad cloud (n=%lld stride=%d)", (long long)n, stride_bytes);
+    if (n >= (1ll << 31) - 1) return fail(PCC_ERR_INVALID, "n=%lld exceeds int32 indices", (long long)n);
+    cudaStream_t s = (cudaStream_t)stream;
+    PCC_CUDA(cudaSetDevice(idx->device));
+    idx->built = false;
+    idx->inv_valid = false;
+    const int64_t m = indices ? n_idx : n;
+    idx->n_input = n;                 // labels / self-query rows are addressed by ORIGINAL row number
+    idx->n_indexed = 0;
+    idx->gh = GridHost();
+
+    const uint8_t *raw = (const uint8_t *)pts;
+    const int32_t *d_indices = indices;
+    if (mem == PCC_HOST && m > 0) {
+        PCC_TRY(idx->raw.reserve((size_t)n * stride_bytes));
+        PCC_CUDA(cudaMemcpyAsync(idx->raw.p, pts, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, s));
+        raw = idx->raw.as<uint8_t>();
+        if (indices) {
+            PCC_TRY(idx->misc.reserve((size_t)n_idx * 4));
+            PCC_CUDA(cudaMemcpyAsync(idx->misc.p, indices, (size_t)n_idx * 4, cudaMemcpyHostToDevice, s));
+            d_indices = idx->misc.as<int32_t>();
+        }
+    }
+    // 1. strided rows -> float4 staging + bbox + finite count
+    int *h = (int *)idx->h_pinned;            // [0..5] bbox, [8..9] n_finite, [10..11] nonzero
+    PCC_TRY(idx->stage4.reserve((size_t)std::max<int64_t>(m, 1) * sizeof(float4)));
+    PCC_TRY(idx->keys64.reserve(256));
+    int *d_scal = idx->keys64.as<int>();      // 6 ints bbox + 2 x u64
+    {
+        int init[12] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, 0, 0, 0, 0, 0, 0};
+        memcpy(h, init, sizeof(init));
+        PCC_CUDA(cudaMemcpyAsync(d_scal, h, sizeof(init), cudaMemcpyHostToDevice, s));
+        PCC_CUDA(cudaStreamSynchronize(s));    // h is reused below
+    }
+    if (m > 0) {
+        extract_kernel<<<blocks_for(m, 256), 256, 0, s>>>(raw, stride_bytes, d_indices, m, n, idx->stage4.as<float4>(), d_scal, (unsigned long long *)(d_scal + 8));
+        PCC_LAUNCHED();
+        PCC_CUDA(cudaGetLastError());
+    }
+    PCC_CUDA(cudaMemcpyAsync(h, d_scal, 48, cudaMemcpyDeviceToHost, s));
+    PCC_CUDA(cudaStreamSynchronize(s));
+    const int64_t nfin = (int64_t)(*(unsigned long long *)(h + 8));
+    idx->n_indexed = nfin;
+    if (nfin == 0) {   // empty index: every query returns nothing
+        PCC_TRY(idx->pts.reserve(sizeof(float4)));
+        PCC_TRY(idx->cell_start.reserve(2 * sizeof(uint32_t)));
+        PCC_CUDA(cudaMemsetAsync(idx->cell_start.p, 0, 2 * sizeof(uint32_t), s));
+        idx->built = true;
+        return PCC_OK;
+    }
+    double lo[3], ext[3];
+    for (int d = 0; d < 3; ++d) { lo[d] = ord2f(h[d]); ext[d] = (double)ord2f(h[3 + d]) - lo[d]; }
+
+    // 2. cell size: caller's hint, or iterate on the measured occupancy of non-empty cells
+    int64_t max_cells = kMaxCellsDefault;
+    if (const char *e = getenv("PCC_MAX_CELLS")) { long long v = atoll(e); if (v >= 1) max_cells = v; }
+    const double mx = std::max(ext[0], std::max(ext[1], ext[2]));
+    double cell;
+    const bool autotune = !(cell_hint > 0);
+    const double target = occupancy_target(k_hint);
+    if (!autotune) cell = cell_hint;
+    else {
+        int live = 0; double vol = 1;
+        for (int d = 0; d < 3; ++d) if (ext[d] > 1e-6 * mx && ext[d] > 0) { ++live; vol *= ext[d]; }
+        cell = live ? std::pow(vol * target / (double)nfin, 1.0 / live) : 1.0;
+    }
+    cell = clamp_cell(ext, cell, max_cells);
+
+    PCC_TRY(idx->cellrank.reserve((size_t)m * sizeof(uint2)));
+    BinParams b{};
+    int dims[3]; int64_t n_cells = 0; double occ = 0;
+    double prev_cell = 0, prev_occ = 0;
+    for (int it = 0; it < 5; ++it) {
+        dims_for(ext, cell, dims);
+        n_cells = (int64_t)dims[0] * dims[1] * dims[2];
+        const float cellf = (float)cell;
+        b = BinParams{(float)lo[0], (float)lo[1], (float)lo[2], 1.0f / cellf, dims[0], dims[1], dims[2]};
+        PCC_TRY(idx->cell_start.reserve((size_t)(n_cells + 1) * sizeof(uint32_t)));
+        PCC_CUDA(cudaMemsetAsync(idx->cell_start.p, 0, (size_t)(n_cells + 1) * sizeof(uint32_t), s));
+        PCC_CUDA(cudaMemsetAsync(d_scal + 10, 0, 8, s));
+        bin_kernel<<<blocks_for(m, 256), 256, 0, s>>>(idx->stage4.as<float4>(), m, b, idx->cell_start.as<uint32_t>(), idx->cellrank.as<uint2>());
+        PCC_LAUNCHED();
+        nonzero_kernel<<<(unsigned)std::min<int64_t>(blocks_for(n_cells, 256), 148 * 16), 256, 0, s>>>(idx->cell_start.as<uint32_t>(), n_cells, (unsigned long long *)(d_scal + 10));
+        PCC_LAUNCHED();
+        PCC_CUDA(cudaGetLastError());
+        PCC_CUDA(cudaMemcpyAsync(h + 10, d_scal + 10, 8, cudaMemcpyDeviceToHost, s));
+        PCC_CUDA(cudaStreamSynchronize(s));
+        const int64_t nonempty = (int64_t)(*(unsigned long long *)(h + 10));
+        occ = (double)nfin / (double)std::max<int64_t>(nonempty, 1);
+        if (!autotune || it == 4) break;
+        if (occ > 0.75 * target && occ < 1.4 * target) break;
+        double dim_est = 2.0;   // first correction assumes a surface; afterwards use the measured scaling exponent
+        if (prev_cell > 0 && prev_occ > 0 && std::fabs(std::log(cell / prev_cell)) > 1e-3) {
+            dim_est = std::log(occ / prev_occ) / std::log(cell / prev_cell);
+            dim_est = std::min(3.0, std::max(1.0, dim_est));
+        }
+        prev_cell = cell; prev_occ = occ;
+        double next = clamp_cell(ext, cell * std::pow(target / occ, 1.0 / dim_est), max_cells);
+        if (std::fabs(next / cell - 1.0) < 0.02) break;   // clamped: cannot get closer
+        cell = next;
+    }
+    idx->gh.ox = b.ox; idx->gh.oy = b.oy; idx->gh.oz = b.oz;
+    idx->gh.cell = (float)cell; idx->gh.inv_cell = b.inv;
+    idx->gh.nx = dims[0]; idx->gh.ny = dims[1]; idx->gh.nz = dims[2];
+    idx->gh.n_cells = n_cells; idx->gh.occupancy = occ;
+
+    // 3. cell-start scan (in place over the histogram) and scatter
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, idx->cell_start.as<uint32_t>(), idx->cell_start.as<uint32_t>(), (int)(n_cells + 1), s);
+    PCC_TRY(idx->cub_tmp.reserve(tmp));
+    PCC_CUDA(cub::DeviceScan::ExclusiveSum(idx->cub_tmp.p, tmp, idx->cell_start.as<uint32_t>(), idx->cell_start.as<uint32_t>(), (int)(n_cells + 1), s));
+    g_launches += 2;
+    PCC_TRY(idx->pts.reserve((size_t)nfin * sizeof(float4)));
+    scatter_kernel<<<blocks_for(m, 256), 256, 0, s>>>(idx->stage4.as<float4>(), idx->cellrank.as<uint2>(), m, idx->cell_start.as<uint32_t>(), idx->pts.as<float4>());
+    PCC_LAUNCHED();
+    PCC_CUDA(cudaGetLastError());
+    if (mem == PCC_HOST) PCC_CUDA(cudaStreamSynchronize(s));
+    idx->built = true;
+    return PCC_OK;
+}
+
+int pcc_export(const pcc_index *idx, double meta[16], void *ptrs[2]) {
+    if (!idx || !idx->built) return fail(PCC_ERR_STATE, "index not built");
+    meta[0] = (double)idx->n_indexed; meta[1] = (double)idx->n_input;
+    meta[2] = idx->gh.nx; meta[3] = idx->gh.ny; meta[4] = idx->gh.nz;
+    meta[5] = idx->gh.ox; meta[6] = idx->gh.oy; meta[7] = idx->gh.oz;
+    meta[8] = idx->gh.cell; meta[9] = idx->gh.inv_cell; meta[10] = idx->gh.occupancy; meta[11] = (double)idx->gh.n_cells;
+    meta[12] = meta[13] = meta[14] = meta[15] = 0;
+    ptrs[0] = idx->pts.p; ptrs[1] = idx->cell_start.p;
+    return PCC_OK;
+}
+
+int pcc_adopt(pcc_index *idx, const double meta[16], void *stream) {
+    if (!idx) return fail(PCC_ERR_INVALID, "idx is NULL");
+    (void)stream;
+    PCC_CUDA(cudaSetDevice(idx->device));
+    idx->n_indexed = (int64_t)meta[0]; idx->n_input = (int64_t)meta[1];
+    idx->gh.nx = (int)meta[2]; idx->gh.ny = (int)meta[3]; idx->gh.nz = (int)meta[4];
+    idx->gh.ox = (float)meta[5]; idx->gh.oy = (float)meta[6]; idx->gh.oz = (float)meta[7];
+    idx->gh.cell = (float)meta[8]; idx->gh.inv_cell = (float)meta[9]; idx->gh.occupancy = meta[10]; idx->gh.n_cells = (int64_t)meta[11];
+    PCC_TRY(idx->pts.reserve((size_t)std::max<int64_t>(idx->n_indexed, 1) * sizeof(float4)));
+    PCC_TRY(idx->cell_start.reserve((size_t)(idx->gh.n_cells + 1) * sizeof(uint32_t)));
+    idx->built = true;
+    idx->inv_valid = false;
+    return PCC_OK;
+}
+
+}  // extern "C"

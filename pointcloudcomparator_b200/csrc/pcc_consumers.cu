@@ -1,0 +1,228 @@
+// pcc_consumers.cu -- the O(1)/O(n) host-driven parts of the consumers: StatisticalOutlierRemoval's second pass,
+// Umeyama from the ICP sums, and the ICP loop itself.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "pcc_internal.h"
+
+namespace pcc {
+
+static inline unsigned nblocks(int64_t n, int threads) { return (unsigned)std::max<int64_t>(1, (n + threads - 1) / threads); }
+
+// per-block (sum d, sum d*d) with the product rounded in fp32 first, as PCL's "sq_sum += distances[i] * distances[i]" does
+__global__ void sor_sums_kernel(const float *__restrict__ d, int64_t n, double *__restrict__ partials) {
+    __shared__ double r0[256], r1[256];
+    double a = 0, b = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) { float v = d[i]; a += (double)v; b += (double)(v * v); }
+    r0[threadIdx.x] = a; r1[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) { r0[threadIdx.x] += r0[threadIdx.x + o]; r1[threadIdx.x] += r1[threadIdx.x + o]; } __syncthreads(); }
+    if (threadIdx.x == 0) { partials[2 * blockIdx.x] = r0[0]; partials[2 * blockIdx.x + 1] = r1[0]; }
+}
+__global__ void sor_final_kernel(const double *__restrict__ partials, int nb, double *__restrict__ out) {
+    if (threadIdx.x < 2) { double v = 0; for (int b = 0; b < nb; ++b) v += partials[2 * b + threadIdx.x]; out[threadIdx.x] = v; }
+}
+__global__ void sor_keep_kernel(const float *__restrict__ d, int64_t n, double thr, uint8_t *__restrict__ keep, unsigned long long *__restrict__ kept) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned k = 0;
+    if (i < n) { k = !((double)d[i] > thr); if (keep) keep[i] = (uint8_t)k; }
+    k = __reduce_add_sync(0xffffffffu, k);
+    if ((threadIdx.x & 31) == 0 && k) atomicAdd(kept, (unsigned long long)k);
+}
+__global__ void xform_kernel(const uint8_t *__restrict__ raw, int stride, int64_t n, const float *__restrict__ Tm, float4 *__restrict__ dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *p = (const float *)(raw + i * (int64_t)stride);
+    const float x = p[0], y = p[1], z = p[2];
+    // pcl::transformPointCloud arithmetic: ((m0*x + m1*y) + m2*z) + m3 (fp32)
+    dst[i] = make_float4(((Tm[0] * x + Tm[1] * y) + Tm[2] * z) + Tm[3], ((Tm[4] * x + Tm[5] * y) + Tm[6] * z) + Tm[7], ((Tm[8] * x + Tm[9] * y) + Tm[10] * z) + Tm[11], 1.f);
+}
+
+// ---- 3x3 SVD in double (Jacobi on A^T A) for Umeyama ----
+static void svd3(const double A[9], double U[9], double S[3], double V[9]) {
+    double B[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += A[3 * k + i] * A[3 * k + j]; B[3 * i + j] = s; }
+    for (int i = 0; i < 9; ++i) V[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        if (std::fabs(B[1]) + std::fabs(B[2]) + std::fabs(B[5]) < 1e-300) break;
+        for (int p = 0; p < 2; ++p) for (int q = p + 1; q < 3; ++q) {
+            const double apq = B[3 * p + q];
+            if (std::fabs(apq) < 1e-300) continue;
+            const double theta = (B[3 * q + q] - B[3 * p + p]) / (2.0 * apq);
+            const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+            const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+            for (int k = 0; k < 3; ++k) { double a = B[3 * k + p], b = B[3 * k + q]; B[3 * k + p] = c * a - s * b; B[3 * k + q] = s * a + c * b; }
+            for (int k = 0; k < 3; ++k) { double a = B[3 * p + k], b = B[3 * q + k]; B[3 * p + k] = c * a - s * b; B[3 * q + k] = s * a + c * b; }
+            for (int k = 0; k < 3; ++k) { double a = V[3 * k + p], b = V[3 * k + q]; V[3 * k + p] = c * a - s * b; V[3 * k + q] = s * a + c * b; }
+        }
+    }
+    const double ev[3] = {B[0], B[4], B[8]};
+    int ord[3] = {0, 1, 2};
+    std::sort(ord, ord + 3, [&](int a, int b) { return ev[a] > ev[b]; });
+    double Vs[9];
+    for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) Vs[3 * r + c] = V[3 * r + ord[c]];
+    memcpy(V, Vs, sizeof(Vs));
+    for (int c = 0; c < 3; ++c) S[c] = std::sqrt(std::max(ev[ord[c]], 0.0));
+    for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) { double s = 0; for (int k = 0; k < 3; ++k) s += A[3 * r + k] * V[3 * k + c]; U[3 * r + c] = s; }
+    bool good[3];
+    for (int c = 0; c < 3; ++c) {
+        const double nrm = std::sqrt(U[c] * U[c] + U[3 + c] * U[3 + c] + U[6 + c] * U[6 + c]);
+        good[c] = nrm > 1e-12 * (S[0] > 0 ? S[0] : 1.0) && nrm > 0;
+        if (good[c]) for (int r = 0; r < 3; ++r) U[3 * r + c] /= nrm;
+    }
+    if (!good[0]) { U[0] = 1; U[3] = 0; U[6] = 0; }
+    if (!good[1]) {
+        const double a[3] = {U[0], U[3], U[6]};
+        const int m = std::fabs(a[0]) < std::fabs(a[1]) ? (std::fabs(a[0]) < std::fabs(a[2]) ? 0 : 2) : (std::fabs(a[1]) < std::fabs(a[2]) ? 1 : 2);
+        double v[3] = {-a[m] * a[0], -a[m] * a[1], -a[m] * a[2]}; v[m] += 1.0;
+        const double nrm = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        U[1] = v[0] / nrm; U[4] = v[1] / nrm; U[7] = v[2] / nrm;
+    }
+    if (!good[2]) {
+        const double a[3] = {U[0], U[3], U[6]}, b[3] = {U[1], U[4], U[7]};
+        U[2] = a[1] * b[2] - a[2] * b[1]; U[5] = a[2] * b[0] - a[0] * b[2]; U[8] = a[0] * b[1] - a[1] * b[0];
+    }
+}
+static double det3(const double *m) { return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]); }
+static void mat4_mul(const float *A, const float *B, float *C) {
+    float r[16];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { float s = 0.f; for (int k = 0; k < 4; ++k) s += A[4 * i + k] * B[4 * k + j]; r[4 * i + j] = s; }
+    memcpy(C, r, sizeof(r));
+}
+
+}  // namespace pcc
+
+using namespace pcc;
+
+extern "C" {
+
+// TransformationEstimationSVD -> pcl::umeyama(src, tgt, with_scaling = false) [up], evaluated from running sums in double.
+int pcc_umeyama_from_sums(const double sums[16], int64_t count, float T16[16]) {
+    if (!sums || !T16 || count < 1) return fail(PCC_ERR_INVALID, "bad sums / count");
+    const double n = (double)count;
+    double ms[3], mt[3], sigma[9];
+    for (int i = 0; i < 3; ++i) { ms[i] = sums[i] / n; mt[i] = sums[3 + i] / n; }
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) sigma[3 * i + j] = sums[6 + 3 * i + j] / n - mt[i] * ms[j];
+    double U[9], S[3], V[9];
+    svd3(sigma, U, S, V);
+    double Sg[3] = {1, 1, 1};
+    if (det3(sigma) < 0) Sg[2] = -1;
+    int rank = 0;
+    for (int i = 0; i < 3; ++i) if (!(std::fabs(S[i]) <= std::fabs(S[0]) * 1e-12)) ++rank;
+    if (rank == 2) Sg[2] = det3(U) * det3(V) > 0 ? 1 : -1;
+    double R[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += U[3 * i + k] * Sg[k] * V[3 * j + k]; R[3 * i + j] = s; }
+    for (int i = 0; i < 16; ++i) T16[i] = (i % 5 == 0) ? 1.f : 0.f;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) T16[4 * i + j] = (float)R[3 * i + j];
+        T16[4 * i + 3] = (float)(mt[i] - (R[3 * i] * ms[0] + R[3 * i + 1] * ms[1] + R[3 * i + 2] * ms[2]));
+    }
+    return PCC_OK;
+}
+
+int pcc_sor_threshold(pcc_index *idx, const float *distances, int64_t n, int64_t n_valid, double std_mul, double stats[3], uint8_t *keep, int64_t *kept, int mem, void *stream) {
+    if (!idx) return fail(PCC_ERR_INVALID, "idx is NULL");
+    if (n < 0 || (n > 0 && !distances) || !stats) return fail(PCC_ERR_INVALID, "bad distances / stats");
+    PCC_CUDA(cudaSetDevice(idx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_valid <= 0) n_valid = n;
+    if (kept) *kept = 0;
+    stats[0] = stats[1] = stats[2] = 0;
+    if (n == 0) return PCC_OK;
+    const float *d = distances;
+    if (mem == PCC_HOST) {
+        PCC_TRY(idx->out_f.reserve((size_t)n * 4));
+        PCC_CUDA(cudaMemcpyAsync(idx->out_f.p, distances, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        d = idx->out_f.as<float>();
+    }
+    const int nb = (int)std::min<int64_t>(nblocks(n, 256), 1024);
+    PCC_TRY(idx->keys64b.reserve((size_t)(2 * nb + 4) * sizeof(double)));
+    double *partials = idx->keys64b.as<double>(), *d_out = partials + 2 * nb;
+    sor_sums_kernel<<<nb, 256, 0, s>>>(d, n, partials); PCC_LAUNCHED();
+    sor_final_kernel<<<1, 32, 0, s>>>(partials, nb, d_out); PCC_LAUNCHED();
+    double *h = (double *)idx->h_pinned;
+    PCC_CUDA(cudaMemcpyAsync(h, d_out, 16, cudaMemcpyDeviceToHost, s));
+    PCC_CUDA(cudaStreamSynchronize(s));
+    const double sum = h[0], sq = h[1], nv = (double)n_valid;
+    const double mean = sum / nv;
+    const double var = (sq - sum * sum / nv) / (nv - 1.0);
+    const double sd = std::sqrt(var);
+    stats[0] = mean; stats[1] = sd; stats[2] = mean + std_mul * sd;
+    uint8_t *dk = keep;
+    if (keep && mem == PCC_HOST) { PCC_TRY(idx->out_i.reserve((size_t)n)); dk = idx->out_i.as<uint8_t>(); }
+    unsigned long long *d_kept = (unsigned long long *)(d_out + 2);
+    PCC_CUDA(cudaMemsetAsync(d_kept, 0, 8, s));
+    sor_keep_kernel<<<nblocks(n, 256), 256, 0, s>>>(d, n, stats[2], dk, d_kept); PCC_LAUNCHED();
+    PCC_CUDA(cudaGetLastError());
+    PCC_CUDA(cudaMemcpyAsync(h, d_kept, 8, cudaMemcpyDeviceToHost, s));
+    if (keep && mem == PCC_HOST) PCC_CUDA(cudaMemcpyAsync(keep, dk, (size_t)n, cudaMemcpyDeviceToHost, s));
+    PCC_CUDA(cudaStreamSynchronize(s));
+    if (kept) *kept = (int64_t)(*(unsigned long long *)h);
+    return PCC_OK;
+}
+
+// IterativeClosestPoint::computeTransformation as the reference configures it (src/comparator.cpp:1089-1099):
+// max_iter iterations, transformation_epsilon 0 (rotation threshold 1.0, translation threshold 0), absolute MSE
+// threshold 1e-12, relative MSE threshold -DBL_MAX (never), no rejectors, no correspondence distance limit.
+int pcc_icp_align(pcc_index *idx, const void *src, int64_t ns, int stride_bytes, int max_iter, float T16[16], int *converged, double *fitness, int *iterations, int mem, void *stream) {
+    if (!idx) return fail(PCC_ERR_INVALID, "idx is NULL");
+    if (!idx->built) return fail(PCC_ERR_STATE, "index not built (call pcc_build first)");
+    if (ns < 0 || (ns > 0 && !src) || stride_bytes < 12 || (stride_bytes & 3) || !T16) return fail(PCC_ERR_INVALID, "bad source cloud");
+    PCC_CUDA(cudaSetDevice(idx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    float Tfinal[16], Tstep[16];
+    for (int i = 0; i < 16; ++i) Tfinal[i] = (i % 5 == 0) ? 1.f : 0.f;
+    int it = 0, conv = 0;
+    double fit = DBL_MAX;
+    // device working copy of the source (float4 rows), moved in place every iteration like PCL's input_transformed
+    const uint8_t *raw = (const uint8_t *)src;
+    if (mem == PCC_HOST && ns > 0) {
+        PCC_TRY(idx->stage4.reserve((size_t)ns * stride_bytes));     // stage4 is free after pcc_build
+        PCC_CUDA(cudaMemcpyAsync(idx->stage4.p, src, (size_t)ns * stride_bytes, cudaMemcpyHostToDevice, s));
+        raw = idx->stage4.as<uint8_t>();
+    }
+    PCC_TRY(idx->parent.reserve((size_t)std::max<int64_t>(ns, 1) * sizeof(float4) + 64));
+    float4 *cur = idx->parent.as<float4>();
+    float *d_T = (float *)(cur + std::max<int64_t>(ns, 1));
+    if (ns > 0) {
+        PCC_CUDA(cudaMemcpyAsync(d_T, Tfinal, 64, cudaMemcpyHostToDevice, s));
+        xform_kernel<<<nblocks(ns, 256), 256, 0, s>>>(raw, stride_bytes, ns, d_T, cur); PCC_LAUNCHED();   // identity: plain copy to float4
+        PCC_CUDA(cudaGetLastError());
+    }
+    double prev_mse = DBL_MAX;
+    const float *apply = nullptr;
+    for (;;) {
+        double sums[16]; int64_t cnt = 0;
+        PCC_TRY(pcc_icp_step(idx, cur, ns, sizeof(float4), apply, sums, &cnt, nullptr, nullptr, PCC_DEVICE, s));
+        if (cnt < 3) { conv = 0; break; }                        // "Not enough correspondences found"
+        PCC_TRY(pcc_umeyama_from_sums(sums, cnt, Tstep));
+        mat4_mul(Tstep, Tfinal, Tfinal);
+        apply = Tstep;                                            // transformCloud is fused into the next pass
+        ++it;
+        if (it >= max_iter) { conv = 1; break; }                  // CONVERGENCE_CRITERIA_ITERATIONS
+        const double cos_angle = 0.5 * ((double)Tstep[0] + (double)Tstep[5] + (double)Tstep[10] - 1);
+        const double tr2 = (double)Tstep[3] * Tstep[3] + (double)Tstep[7] * Tstep[7] + (double)Tstep[11] * Tstep[11];
+        if (cos_angle >= 1.0 && tr2 <= 0.0) { conv = 1; break; } // CONVERGENCE_CRITERIA_TRANSFORM
+        const double mse = sums[15] / (double)cnt;
+        if (std::fabs(mse - prev_mse) < 1e-12) { conv = 1; break; }   // CONVERGENCE_CRITERIA_ABS_MSE
+        prev_mse = mse;
+    }
+    // getFitnessScore: ORIGINAL source moved by the final transform, mean 1-NN squared distance
+    if (ns > 0) {
+        PCC_CUDA(cudaMemcpyAsync(d_T, Tfinal, 64, cudaMemcpyHostToDevice, s));
+        xform_kernel<<<nblocks(ns, 256), 256, 0, s>>>(raw, stride_bytes, ns, d_T, cur); PCC_LAUNCHED();
+        PCC_CUDA(cudaGetLastError());
+        double sums[16]; int64_t cnt = 0;
+        PCC_TRY(pcc_icp_step(idx, cur, ns, sizeof(float4), nullptr, sums, &cnt, nullptr, nullptr, PCC_DEVICE, s));
+        if (cnt > 0) fit = sums[15] / (double)cnt;
+    }
+    memcpy(T16, Tfinal, sizeof(Tfinal));
+    if (converged) *converged = conv;
+    if (fitness) *fitness = fit;
+    if (iterations) *iterations = it;
+    return PCC_OK;
+}
+
+}  // extern "C"

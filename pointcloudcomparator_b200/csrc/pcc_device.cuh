@@ -1,0 +1,255 @@
+// pcc_device.cuh -- device-side building blocks shared by every query kernel.
+//
+// Data layout in HBM: the indexed cloud is ONE float4 array sorted by grid cell
+// (x, y, z, original index bit-cast into .w) plus ONE dense uint32 cell_start table in row-major
+// (z, y, x) order, so the cells x-R..x+R of a row are one contiguous run of points: a 3x3x3 stencil
+// is 9 coalesced float4 runs, not 27 cell lookups.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math_constants.h>
+
+namespace pcc {
+
+struct Grid {
+    const float4 *pts;            // sorted by cell; .w = original index (int bits)
+    const uint32_t *cell_start;   // n_cells + 1
+    float ox, oy, oz;             // origin = bbox min
+    float inv_cell, cell;
+    int nx, ny, nz;
+    uint32_t n;                   // indexed points
+};
+
+// Squared L2 exactly as FLANN L2_Simple evaluates it in fp32: ((dx*dx + dy*dy) + dz*dz), no FMA.
+__device__ __forceinline__ float dist2(float qx, float qy, float qz, float px, float py, float pz) {
+    float dx = __fsub_rn(qx, px), dy = __fsub_rn(qy, py), dz = __fsub_rn(qz, pz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+// continuous grid coordinate; the SAME expression bins points at build time and queries at search time
+__device__ __forceinline__ float grid_u(float x, float o, float inv) { return __fmul_rn(__fsub_rn(x, o), inv); }
+__device__ __forceinline__ int grid_c(float u, int n) { return (int)fminf(fmaxf(floorf(u), 0.f), (float)(n - 1)); }
+__device__ __forceinline__ bool finite3(float x, float y, float z) { return isfinite(x) && isfinite(y) && isfinite(z); }
+
+struct QueryCell {
+    float ux, uy, uz;
+    int cx, cy, cz;
+};
+__device__ __forceinline__ QueryCell locate(const Grid &g, float x, float y, float z) {
+    QueryCell c;
+    c.ux = grid_u(x, g.ox, g.inv_cell); c.uy = grid_u(y, g.oy, g.inv_cell); c.uz = grid_u(z, g.oz, g.inv_cell);
+    c.cx = grid_c(c.ux, g.nx); c.cy = grid_c(c.uy, g.ny); c.cz = grid_c(c.uz, g.nz);
+    return c;
+}
+// Squared world distance below which every indexed point is guaranteed to lie inside the block of
+// Chebyshev radius R around the query's cell (+inf once the block covers the whole grid).
+// Margins: 2e-3 cells absolute + 1e-5 relative cover the fp32 rounding of grid_u (dims are capped
+// at 2048 cells per axis, so |u| rounding <= 2048 * 2^-23 = 2.5e-4) and of cell = 1 / inv_cell.
+__device__ __forceinline__ float covered_d2(const Grid &g, const QueryCell &c, int R) {
+    float b = CUDART_INF_F;
+    if (c.cx - R > 0) b = fminf(b, c.ux - (float)(c.cx - R));
+    if (c.cx + R < g.nx - 1) b = fminf(b, (float)(c.cx + R + 1) - c.ux);
+    if (c.cy - R > 0) b = fminf(b, c.uy - (float)(c.cy - R));
+    if (c.cy + R < g.ny - 1) b = fminf(b, (float)(c.cy + R + 1) - c.uy);
+    if (c.cz - R > 0) b = fminf(b, c.uz - (float)(c.cz - R));
+    if (c.cz + R < g.nz - 1) b = fminf(b, (float)(c.cz + R + 1) - c.uz);
+    if (b == CUDART_INF_F) return b;
+    b = (b * (1.0f - 1e-5f) - 2e-3f) * g.cell;
+    return b > 0.f ? b * b : 0.f;
+}
+
+// Visit every indexed point in the cells with Chebyshev ring index in (Rin, Rout] around (cx,cy,cz)
+// (Rin = -1 visits the whole block).  f(pos, float4 point).
+template <class F>
+__device__ __forceinline__ void scan_shell(const Grid &g, const QueryCell &c, int Rin, int Rout, F &&f) {
+    const int z0 = max(c.cz - Rout, 0), z1 = min(c.cz + Rout, g.nz - 1);
+    const int y0 = max(c.cy - Rout, 0), y1 = min(c.cy + Rout, g.ny - 1);
+    const int xa = max(c.cx - Rout, 0), xb = min(c.cx + Rout, g.nx - 1);
+    for (int z = z0; z <= z1; ++z) {
+        for (int y = y0; y <= y1; ++y) {
+            const uint32_t *row = g.cell_start + ((size_t)z * g.ny + y) * g.nx;
+            const bool outer = max(abs(z - c.cz), abs(y - c.cy)) > Rin;
+            if (outer) {
+                uint32_t j = __ldg(row + xa), e = __ldg(row + xb + 1);
+                for (; j < e; ++j) f(j, __ldg(g.pts + j));
+            } else {
+                int xl = c.cx - Rin - 1;             // left strip [xa, xl]
+                if (xl >= xa) { uint32_t j = __ldg(row + xa), e = __ldg(row + xl + 1); for (; j < e; ++j) f(j, __ldg(g.pts + j)); }
+                int xr = c.cx + Rin + 1;             // right strip [xr, xb]
+                if (xr <= xb) { uint32_t j = __ldg(row + xr), e = __ldg(row + xb + 1); for (; j < e; ++j) f(j, __ldg(g.pts + j)); }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// top-k containers.  Entries are 64-bit keys (fp32 d2 bits << 32 | payload): d2 >= +0 so the
+// unsigned order of the bits is the numeric order, and one 64-bit compare gives the canonical
+// (d2, original index) tie rule.  Empty slots hold ~0 (decodes to idx -1, d2 +inf on output).
+typedef unsigned long long nkey_t;
+#define PCC_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+__device__ __forceinline__ nkey_t make_key(float d2, uint32_t payload) { return ((nkey_t)__float_as_uint(d2) << 32) | payload; }
+__device__ __forceinline__ float key_d2(nkey_t k) { return k == PCC_EMPTY_KEY ? CUDART_INF_F : __uint_as_float((uint32_t)(k >> 32)); }
+__device__ __forceinline__ int32_t key_idx(nkey_t k) { return k == PCC_EMPTY_KEY ? -1 : (int32_t)(uint32_t)k; }
+
+// k <= K entries kept sorted in registers (all indexing is compile-time after unrolling)
+template <int K>
+struct RegList {
+    nkey_t key[K];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < K; ++i) key[i] = PCC_EMPTY_KEY;
+    }
+    __device__ __forceinline__ void offer(nkey_t c) {
+        if (c < key[K - 1]) {
+#pragma unroll
+            for (int i = 0; i < K; ++i) { const nkey_t t = key[i]; const bool lt = c < t; key[i] = lt ? c : t; c = lt ? t : c; }
+        }
+    }
+    __device__ __forceinline__ nkey_t at(int j) const {   // j runtime, resolved with selects
+        nkey_t r = key[0];
+#pragma unroll
+        for (int i = 1; i < K; ++i) r = (i == j) ? key[i] : r;
+        return r;
+    }
+    __device__ __forceinline__ void finish() {}
+};
+
+// k entries as a binary max-heap in shared memory, slot-major ([slot][thread]) so that the 32 lanes
+// of a warp always hit 32 different banks whatever slot each lane is at.  Used for 32 < k <= PCC_MAX_K.
+struct HeapList {
+    nkey_t *h; int stride; int k; int cnt;
+    __device__ __forceinline__ nkey_t &a(int i) { return h[(size_t)i * stride]; }
+    __device__ __forceinline__ void init(nkey_t *base, int stride_, int k_) { h = base; stride = stride_; k = k_; cnt = 0; }
+    __device__ __forceinline__ void offer(nkey_t c) {
+        if (cnt < k) {                       // sift up
+            int i = cnt++;
+            while (i > 0) { int p = (i - 1) >> 1; nkey_t pv = a(p); if (!(pv < c)) break; a(i) = pv; i = p; }
+            a(i) = c;
+        } else if (c < a(0)) {               // replace the root, sift down
+            sift_down(c, cnt);
+        }
+    }
+    __device__ __forceinline__ void sift_down(nkey_t c, int n) {
+        int i = 0;
+        for (;;) {
+            int l = 2 * i + 1; if (l >= n) break;
+            nkey_t lv = a(l); int m = l;
+            if (l + 1 < n) { nkey_t rv = a(l + 1); if (lv < rv) { lv = rv; m = l + 1; } }
+            if (!(c < lv)) break;
+            a(i) = lv; i = m;
+        }
+        a(i) = c;
+    }
+    __device__ __forceinline__ bool full() const { return cnt == k; }
+    __device__ __forceinline__ nkey_t worst() { return cnt == k ? a(0) : PCC_EMPTY_KEY; }
+    // heap -> ascending order in slots [0, cnt); slots [cnt, k) = empty
+    __device__ __forceinline__ void finish() {
+        for (int n = cnt - 1; n > 0; --n) { nkey_t last = a(n); a(n) = a(0); sift_down(last, n); }
+        for (int i = cnt; i < k; ++i) a(i) = PCC_EMPTY_KEY;
+    }
+    __device__ __forceinline__ nkey_t at(int j) { return a(j); }
+};
+
+// distances only (no payload): k smallest d2 kept sorted in registers with min/max only.
+template <int K>
+struct RegDist {
+    float d[K];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < K; ++i) d[i] = CUDART_INF_F;
+    }
+    __device__ __forceinline__ void offer(float c) {
+        if (c < d[K - 1]) {
+#pragma unroll
+            for (int i = K - 1; i > 0; --i) d[i] = fminf(d[i], fmaxf(d[i - 1], c));
+            d[0] = fminf(d[0], c);
+        }
+    }
+    __device__ __forceinline__ float at(int j) const {
+        float r = d[0];
+#pragma unroll
+        for (int i = 1; i < K; ++i) r = (i == j) ? d[i] : r;
+        return r;
+    }
+};
+
+// -------------------------------------------------------------------------------------------------
+// pcl::eigen33 smallest eigenpair + curvature, fp32, same operation order as the PCL 1.7 source the
+// oracle restates (common/impl/eigen.hpp [up]); compiled with -fmad=false so nothing is contracted.
+__device__ __forceinline__ void roots2(float b, float c, float *r) {
+    r[0] = 0.f;
+    float d = (float)((double)b * (double)b - 4.0 * (double)c);
+    if (d < 0.0f) d = 0.0f;
+    float sd = sqrtf(d);
+    r[2] = 0.5f * (b + sd);
+    r[1] = 0.5f * (b - sd);
+}
+__device__ __forceinline__ void roots3(const float *m, float *r) {
+    float c0 = m[0] * m[4] * m[8] + 2.0f * m[1] * m[2] * m[5] - m[0] * m[5] * m[5] - m[4] * m[2] * m[2] - m[8] * m[1] * m[1];
+    float c1 = m[0] * m[4] - m[1] * m[1] + m[0] * m[8] - m[2] * m[2] + m[4] * m[8] - m[5] * m[5];
+    float c2 = m[0] + m[4] + m[8];
+    if (fabsf(c0) < 1.1920929e-07f) { roots2(c2, c1, r); return; }
+    const float s_inv3 = (float)(1.0 / 3.0);
+    const float s_sqrt3 = sqrtf(3.0f);
+    float c2_over_3 = c2 * s_inv3;
+    float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+    if (a_over_3 > 0.f) a_over_3 = 0.f;
+    float half_b = 0.5f * (c0 + c2_over_3 * (2.0f * c2_over_3 * c2_over_3 - c1));
+    float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+    if (q > 0.f) q = 0.f;
+    float rho = sqrtf(-a_over_3);
+    float theta = atan2f(sqrtf(-q), half_b) * s_inv3;
+    float cos_theta = cosf(theta), sin_theta = sinf(theta);
+    r[0] = c2_over_3 + 2.0f * rho * cos_theta;
+    r[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+    r[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+    float t;
+    if (r[0] >= r[1]) { t = r[0]; r[0] = r[1]; r[1] = t; }
+    if (r[1] >= r[2]) { t = r[1]; r[1] = r[2]; r[2] = t; if (r[0] >= r[1]) { t = r[0]; r[0] = r[1]; r[1] = t; } }
+    if (r[0] <= 0.f) roots2(c2, c1, r);
+}
+// accu[9] = sums in neighbour order (xx xy xz yy yz zz x y z), cnt neighbours -> normal + curvature, flipped to viewpoint
+__device__ __forceinline__ float4 normal_from_accu(float *a, int cnt, float px, float py, float pz, float vx, float vy, float vz) {
+    const float qnan = CUDART_NAN_F;
+    if (cnt < 3) return make_float4(qnan, qnan, qnan, qnan);
+    const float fn = (float)cnt;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a[i] = __fdiv_rn(a[i], fn);
+    float cov[9];
+    cov[0] = a[0] - a[6] * a[6]; cov[1] = a[1] - a[6] * a[7]; cov[2] = a[2] - a[6] * a[8];
+    cov[4] = a[3] - a[7] * a[7]; cov[5] = a[4] - a[7] * a[8]; cov[8] = a[5] - a[8] * a[8];
+    cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+    float scale = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) scale = fmaxf(scale, fabsf(cov[i]));
+    if (scale <= 1.17549435e-38f) scale = 1.0f;
+    float m[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) m[i] = __fdiv_rn(cov[i], scale);
+    float r[3]; roots3(m, r);
+    const float ev = r[0] * scale;
+    m[0] -= r[0]; m[4] -= r[0]; m[8] -= r[0];
+    float v1[3] = {m[1] * m[5] - m[2] * m[4], m[2] * m[3] - m[0] * m[5], m[0] * m[4] - m[1] * m[3]};
+    float v2[3] = {m[1] * m[8] - m[2] * m[7], m[2] * m[6] - m[0] * m[8], m[0] * m[7] - m[1] * m[6]};
+    float v3[3] = {m[4] * m[8] - m[5] * m[7], m[5] * m[6] - m[3] * m[8], m[3] * m[7] - m[4] * m[6]};
+    float l1 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2];
+    float l2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
+    float l3 = v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2];
+    float nx, ny, nz, l;
+    if (l1 >= l2 && l1 >= l3) { nx = v1[0]; ny = v1[1]; nz = v1[2]; l = l1; }
+    else if (l2 >= l1 && l2 >= l3) { nx = v2[0]; ny = v2[1]; nz = v2[2]; l = l2; }
+    else { nx = v3[0]; ny = v3[1]; nz = v3[2]; l = l3; }
+    const float s = sqrtf(l);
+    nx = __fdiv_rn(nx, s); ny = __fdiv_rn(ny, s); nz = __fdiv_rn(nz, s);
+    const float eig_sum = cov[0] + cov[4] + cov[8];
+    const float curv = eig_sum != 0.f ? fabsf(__fdiv_rn(ev, eig_sum)) : 0.f;
+    const float wx = vx - px, wy = vy - py, wz = vz - pz;
+    const float cos_theta = (wx * nx + wy * ny + wz * nz);
+    if (cos_theta < 0) { nx *= -1; ny *= -1; nz *= -1; }
+    return make_float4(nx, ny, nz, curv);
+}
+__device__ __forceinline__ void accu_add(float *a, float x, float y, float z) {
+    a[0] += x * x; a[1] += x * y; a[2] += x * z; a[3] += y * y; a[4] += y * z; a[5] += z * z; a[6] += x; a[7] += y; a[8] += z;
+}
+
+}  // namespace pcc

@@ -1,0 +1,98 @@
+// pcc_internal.h -- host-side state behind the opaque pcc_index of include/pcc/search.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/pcc/search.h"
+#include "pcc_device.cuh"
+
+namespace pcc {
+
+extern thread_local std::string g_error;
+extern int64_t g_launches;
+int fail(int code, const char *fmt, ...);
+
+#define PCC_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess) return pcc::fail(PCC_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+    } while (0)
+#define PCC_TRY(expr)                 \
+    do {                              \
+        int r__ = (expr);             \
+        if (r__ != PCC_OK) return r__; \
+    } while (0)
+#define PCC_LAUNCHED() (++pcc::g_launches)
+
+// grow-only device buffer
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return PCC_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return fail(PCC_ERR_CUDA, "cudaMalloc(%zu) -> %s", want, cudaGetErrorString(e)); }
+        cap = want;
+        return PCC_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+struct GridHost {
+    float ox = 0, oy = 0, oz = 0, cell = 1, inv_cell = 1;
+    int nx = 1, ny = 1, nz = 1;
+    double occupancy = 0;      // mean points per non-empty cell
+    int64_t n_cells = 1;
+};
+
+}  // namespace pcc
+
+struct pcc_index {
+    int device = 0;
+    bool built = false;
+    int64_t n_input = 0;      // rows handed to pcc_build (label / self-query row count)
+    int64_t n_indexed = 0;    // finite rows
+    pcc::GridHost gh;
+    pcc::Buf pts;             // float4 [n_indexed], sorted by cell
+    pcc::Buf cell_start;      // uint32 [n_cells + 1]
+    // scratch (grow-only, reused by every call on this index; calls on one index are serialised by the caller per stream)
+    pcc::Buf raw, stage4, cellrank, qbuf, qkeys, qkeys2, qperm, qperm2, cub_tmp, out_i, out_f, out_l, keys64, keys64b, misc, parent, inv_pos;
+    bool inv_valid = false;   // inv_pos (original row -> sorted position) is built lazily by the consumers that need it
+    void *h_pinned = nullptr;  // 4 KiB pinned scratch for scalar read-backs
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing = false;
+    double last_ms = -1;
+
+    pcc::Grid grid() const {
+        pcc::Grid g;
+        g.pts = pts.as<float4>(); g.cell_start = cell_start.as<uint32_t>();
+        g.ox = gh.ox; g.oy = gh.oy; g.oz = gh.oz; g.inv_cell = gh.inv_cell; g.cell = gh.cell;
+        g.nx = gh.nx; g.ny = gh.ny; g.nz = gh.nz; g.n = (uint32_t)n_indexed;
+        return g;
+    }
+};
+
+namespace pcc {
+// prepared query batch: float4 queries on device + the processing order
+struct Queries {
+    const float4 *q = nullptr;     // [nq] (x, y, z, _)
+    const uint32_t *order = nullptr;  // [nq] query rows sorted by grid cell (non-finite last); nullptr in self mode
+    int64_t nq = 0;
+    bool self = false;             // queries are the indexed cloud itself: thread t handles sorted point t, row = original index
+    int64_t rows = 0;              // number of output rows (nq, or n_input in self mode)
+};
+int prepare_queries(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int mem, cudaStream_t s, Queries *out);
+int copy_out(void *dst, const void *src_dev, size_t bytes, int mem, cudaStream_t s);
+int rebuild_inverse(pcc_index *idx, cudaStream_t s);
+struct KernelTimer {
+    pcc_index *idx; cudaStream_t s;
+    KernelTimer(pcc_index *i, cudaStream_t st) : idx(i), s(st) { if (idx->timing) cudaEventRecord(idx->ev0, s); }
+    void stop() { if (idx->timing) { cudaEventRecord(idx->ev1, s); cudaEventSynchronize(idx->ev1); float ms = 0; cudaEventElapsedTime(&ms, idx->ev0, idx->ev1); idx->last_ms = ms; } }
+};
+}  // namespace pcc

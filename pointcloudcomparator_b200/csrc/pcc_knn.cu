@@ -1,0 +1,483 @@
+// pcc_knn.cu -- batched exact k-nearest-neighbour kernels and the consumers fused onto them.
+//
+// Replaces: a2 Search::nearestKSearch batched over all query points, a5 the first pass of
+// StatisticalOutlierRemoval, a4 NormalEstimation with setKSearch, a6 the ICP correspondence + sums pass,
+// a8 RegionGrowing(RGB)::findPointNeighbours (= pcc_knn with q == NULL).
+//
+// One thread owns one query.  Queries are processed in grid-cell order (the indexed cloud is already
+// sorted; external batches are radix-sorted by cell key) so the 32 lanes of a warp walk overlapping
+// float4 runs that stay in L1.  The search starts with the 3x3x3 block and grows ring by ring until the
+// k-th distance is provably inside the scanned block (covered_d2), so results are exact for any density.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "pcc_internal.h"
+
+namespace pcc {
+
+struct QueryView {
+    const float4 *q; const uint32_t *order; int64_t nq; bool self;
+};
+// thread t -> (query coordinates, output row); returns false for tail threads and non-finite queries
+__device__ __forceinline__ bool load_query(const Grid &g, const QueryView &v, int64_t t, float &x, float &y, float &z, int64_t &row, bool &write_empty) {
+    write_empty = false;
+    if (t >= v.nq) return false;
+    if (v.self) { float4 p = __ldg(g.pts + t); x = p.x; y = p.y; z = p.z; row = __float_as_int(p.w); return true; }
+    uint32_t qi = v.order ? __ldg(v.order + t) : (uint32_t)t;
+    float4 p = __ldg(v.q + qi); x = p.x; y = p.y; z = p.z; row = qi;
+    if (!finite3(x, y, z) || g.n == 0) { write_empty = true; return false; }
+    return true;
+}
+
+// exact kNN driver: scan the 3x3x3 block, then shells, until the k-th key is inside the covered radius
+template <class List>
+__device__ __forceinline__ void knn_search(const Grid &g, float x, float y, float z, int k, List &list) {
+    const QueryCell c = locate(g, x, y, z);
+    int Rin = -1, R = 1;
+    for (;;) {
+        scan_shell(g, c, Rin, R, [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
+        const float cov = covered_d2(g, c, R);
+        if (cov == CUDART_INF_F) break;
+        const nkey_t kth = list.at(k - 1);
+        if (kth != PCC_EMPTY_KEY && key_d2(kth) < cov) break;
+        Rin = R; ++R;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) knn_reg_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float x, y, z; int64_t row; bool empty;
+    RegList<K> list; list.init();
+    const bool live = load_query(g, v, t, x, y, z, row, empty);
+    if (!live && !empty) return;
+    if (live) knn_search(g, x, y, z, k, list);
+    int32_t *oi = out_idx + row * k; float *od = out_d2 + row * k;
+    if (vec4 && K >= 4 && k == K) {
+#pragma unroll
+        for (int j = 0; j + 3 < K; j += 4) {
+            reinterpret_cast<int4 *>(oi)[j >> 2] = make_int4(key_idx(list.key[j]), key_idx(list.key[j + 1]), key_idx(list.key[j + 2]), key_idx(list.key[j + 3]));
+            reinterpret_cast<float4 *>(od)[j >> 2] = make_float4(key_d2(list.key[j]), key_d2(list.key[j + 1]), key_d2(list.key[j + 2]), key_d2(list.key[j + 3]));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j) if (j < k) { oi[j] = key_idx(list.key[j]); od[j] = key_d2(list.key[j]); }
+    }
+}
+
+// 32 < k <= PCC_MAX_K: per-thread max-heap in dynamic shared memory
+__global__ void knn_heap_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2) {
+    extern __shared__ nkey_t smem_keys[];
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float x, y, z; int64_t row; bool empty;
+    HeapList list; list.init(smem_keys + threadIdx.x, blockDim.x, k);
+    const bool live = load_query(g, v, t, x, y, z, row, empty);
+    if (!live && !empty) return;
+    if (live) {
+        const QueryCell c = locate(g, x, y, z);
+        int Rin = -1, R = 1;
+        for (;;) {
+            scan_shell(g, c, Rin, R, [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
+            const float cov = covered_d2(g, c, R);
+            if (cov == CUDART_INF_F) break;
+            if (list.full() && key_d2(list.worst()) < cov) break;
+            Rin = R; ++R;
+        }
+    }
+    list.finish();
+    int32_t *oi = out_idx + row * k; float *od = out_d2 + row * k;
+    for (int j = 0; j < k; ++j) { nkey_t e = list.at(j); oi[j] = key_idx(e); od[j] = key_d2(e); }
+}
+
+// ---- fused: StatisticalOutlierRemoval first pass (mean distance to the mean_k nearest, self dropped) ----
+// EXACT: mean_k == K - 1 (the instantiated sizes match mean_k = 1, 4, 8, 16, 32, 50), every list index is static.
+template <int K, bool EXACT>
+__global__ void __launch_bounds__(128) mean_dist_reg_kernel(Grid g, QueryView v, int mean_k, float *__restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float x, y, z; int64_t row; bool empty;
+    const bool live = load_query(g, v, t, x, y, z, row, empty);
+    if (!live) { if (empty) out[row] = 0.f; return; }
+    RegDist<K> list; list.init();
+    const QueryCell c = locate(g, x, y, z);
+    int Rin = -1, R = 1;
+    for (;;) {
+        scan_shell(g, c, Rin, R, [&](uint32_t, float4 p) { list.offer(dist2(x, y, z, p.x, p.y, p.z)); });
+        const float cov = covered_d2(g, c, R);
+        if (cov == CUDART_INF_F) break;
+        if ((EXACT ? list.d[K - 1] : list.at(mean_k)) < cov) break;
+        Rin = R; ++R;
+    }
+    double s = 0.0;
+    if (EXACT) {
+#pragma unroll
+        for (int j = 1; j < K; ++j) s += sqrt((double)list.d[j]);
+    } else {
+#pragma unroll 1
+        for (int j = 1; j <= mean_k; ++j) s += sqrt((double)list.at(j));
+    }
+    out[row] = (float)(s / (double)mean_k);
+}
+__global__ void mean_dist_heap_kernel(Grid g, QueryView v, int mean_k, float *__restrict__ out) {
+    extern __shared__ nkey_t smem_keys[];
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float x, y, z; int64_t row; bool empty;
+    const bool live = load_query(g, v, t, x, y, z, row, empty);
+    if (!live) { if (empty) out[row] = 0.f; return; }
+    HeapList list; list.init(smem_keys + threadIdx.x, blockDim.x, mean_k + 1);
+    const QueryCell c = locate(g, x, y, z);
+    int Rin = -1, R = 1;
+    for (;;) {
+        scan_shell(g, c, Rin, R, [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
+        const float cov = covered_d2(g, c, R);
+        if (cov == CUDART_INF_F) break;
+        if (list.full() && key_d2(list.worst()) < cov) break;
+        Rin = R; ++R;
+    }
+    list.finish();
+    double s = 0.0;
+    for (int j = 1; j <= mean_k; ++j) s += sqrt((double)key_d2(list.at(j)));
+    out[row] = (float)(s / (double)mean_k);
+}
+
+// ---- fused: NormalEstimation with setKSearch(k) ----
+template <int K>
+__global__ void __launch_bounds__(128) normals_knn_reg_kernel(Grid g, QueryView v, int k, const uint32_t *__restrict__ inv_pos, float vx, float vy, float vz, float4 *__restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float x, y, z; int64_t row; bool empty;
+    const bool live = load_query(g, v, t, x, y, z, row, empty);
+    if (!live) { if (empty) out[row] = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F); return; }
+    RegList<K> list; list.init();
+    knn_search(g, x, y, z, k, list);
+    float a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) if (j < k && list.key[j] != PCC_EMPTY_KEY) { float4 p = __ldg(g.pts + __ldg(inv_pos + (uint32_t)list.key[j])); accu_add(a, p.x, p.y, p.z); ++cnt; }
+    out[row] = normal_from_accu(a, cnt, x, y, z, vx, vy, vz);
+}
+__global__ void normals_knn_heap_kernel(Grid g, QueryView v, int k, const uint32_t *__restrict__ inv_pos, float vx, float vy, float vz, float4 *__restrict__ out) {
+    extern __shared__ nkey_t smem_keys[];
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float x, y, z; int64_t row; bool empty;
+    const bool live = load_query(g, v, t, x, y, z, row, empty);
+    if (!live) { if (empty) out[row] = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F); return; }
+    HeapList list; list.init(smem_keys + threadIdx.x, blockDim.x, k);
+    const QueryCell c = locate(g, x, y, z);
+    int Rin = -1, R = 1;
+    for (;;) {
+        scan_shell(g, c, Rin, R, [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
+        const float cov = covered_d2(g, c, R);
+        if (cov == CUDART_INF_F) break;
+        if (list.full() && key_d2(list.worst()) < cov) break;
+        Rin = R; ++R;
+    }
+    list.finish();
+    float a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; int cnt = 0;
+    for (int j = 0; j < list.cnt; ++j) { float4 p = __ldg(g.pts + __ldg(inv_pos + (uint32_t)list.at(j))); accu_add(a, p.x, p.y, p.z); ++cnt; }
+    out[row] = normal_from_accu(a, cnt, x, y, z, vx, vy, vz);
+}
+
+// ---- fused: ICP correspondence pass ----
+struct Mat34 { float m[12]; };
+static constexpr int kIcpThreads = 128;
+// One thread per source point: move it by T (IterativeClosestPoint::transformCloud arithmetic), find its nearest
+// target point, and reduce the 16 sums Umeyama needs + the correspondence count to one row of doubles per block.
+__global__ void __launch_bounds__(kIcpThreads) icp_step_kernel(Grid g, float4 *__restrict__ src, const uint32_t *__restrict__ order, int64_t ns, Mat34 T, int apply,
+                                                               double *__restrict__ partials, int32_t *__restrict__ corr_idx, float *__restrict__ corr_d2) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[17];
+#pragma unroll
+    for (int i = 0; i < 17; ++i) acc[i] = 0.0;
+    if (t < ns) {
+        const uint32_t qi = order ? __ldg(order + t) : (uint32_t)t;
+        float4 p = src[qi];
+        int32_t bi = -1; float bd = CUDART_INF_F;
+        if (finite3(p.x, p.y, p.z)) {
+            if (apply) {   // ((m0*x + m1*y) + m2*z) + m3 in fp32; -fmad=false keeps the products separately rounded
+                float nx = ((T.m[0] * p.x + T.m[1] * p.y) + T.m[2] * p.z) + T.m[3];
+                float ny = ((T.m[4] * p.x + T.m[5] * p.y) + T.m[6] * p.z) + T.m[7];
+                float nz = ((T.m[8] * p.x + T.m[9] * p.y) + T.m[10] * p.z) + T.m[11];
+                p.x = nx; p.y = ny; p.z = nz;
+                src[qi] = p;
+            }
+            if (g.n > 0 && finite3(p.x, p.y, p.z)) {
+                nkey_t best = PCC_EMPTY_KEY; uint32_t bpos = 0;
+                const QueryCell c = locate(g, p.x, p.y, p.z);
+                int Rin = -1, R = 1;
+                for (;;) {
+                    scan_shell(g, c, Rin, R, [&](uint32_t pos, float4 r) {
+                        const nkey_t k = make_key(dist2(p.x, p.y, p.z, r.x, r.y, r.z), __float_as_uint(r.w));
+                        if (k < best) { best = k; bpos = pos; }
+                    });
+                    const float cov = covered_d2(g, c, R);
+                    if (cov == CUDART_INF_F) break;
+                    if (best != PCC_EMPTY_KEY && key_d2(best) < cov) break;
+                    Rin = R; ++R;
+                }
+                bi = key_idx(best); bd = key_d2(best);
+                if (bi >= 0) {
+                    const float4 m = __ldg(g.pts + bpos);
+                    const double sx = p.x, sy = p.y, sz = p.z, tx = m.x, ty = m.y, tz = m.z;
+                    acc[0] = sx; acc[1] = sy; acc[2] = sz; acc[3] = tx; acc[4] = ty; acc[5] = tz;
+                    acc[6] = tx * sx; acc[7] = tx * sy; acc[8] = tx * sz;
+                    acc[9] = ty * sx; acc[10] = ty * sy; acc[11] = ty * sz;
+                    acc[12] = tz * sx; acc[13] = tz * sy; acc[14] = tz * sz;
+                    acc[15] = (double)bd; acc[16] = 1.0;
+                }
+            }
+        }
+        if (corr_idx) corr_idx[qi] = bi;
+        if (corr_d2) corr_d2[qi] = bd;
+    }
+    __shared__ double red[kIcpThreads / 32][17];
+#pragma unroll
+    for (int i = 0; i < 17; ++i) {
+        double v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 17) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kIcpThreads / 32; ++w) v += red[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * 17 + threadIdx.x] = v;
+    }
+}
+// fixed-order final reduction of the per-block rows (deterministic run to run)
+__global__ void icp_reduce_kernel(const double *__restrict__ partials, int64_t n_blocks, double *__restrict__ out) {
+    __shared__ double red[256];
+    const int comp = blockIdx.x;    // 0..16
+    double v = 0.0;
+    for (int64_t b = threadIdx.x; b < n_blocks; b += blockDim.x) v += partials[(size_t)b * 17 + comp];
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) out[comp] = red[0];
+}
+// strided rows -> float4 working copy of the source cloud
+__global__ void icp_load_kernel(const uint8_t *__restrict__ raw, int stride, int64_t ns, float4 *__restrict__ dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    const float *p = (const float *)(raw + i * (int64_t)stride);
+    dst[i] = make_float4(p[0], p[1], p[2], 1.0f);
+}
+__global__ void icp_store_kernel(const float4 *__restrict__ srcw, int64_t ns, uint8_t *__restrict__ raw, int stride) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    float *p = (float *)(raw + i * (int64_t)stride);
+    float4 v = srcw[i];
+    p[0] = v.x; p[1] = v.y; p[2] = v.z;
+}
+
+__global__ void fill_f32_kernel(float *p, int64_t n, float v) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+static inline unsigned nblocks(int64_t n, int threads) { return (unsigned)std::max<int64_t>(1, (n + threads - 1) / threads); }
+static inline QueryView view_of(const Queries &q) { return QueryView{q.q, q.order, q.nq, q.self}; }
+static int heap_threads(int k) {
+    int t = (int)((96 * 1024) / ((size_t)k * sizeof(nkey_t)));
+    t = std::min(128, (t / 32) * 32);
+    return std::max(32, t);
+}
+template <class Kern>
+static int set_heap_smem(Kern kern) {
+    static bool done = false;   // per kernel instantiation
+    if (!done) { PCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); done = true; }
+    return PCC_OK;
+}
+
+template <int K>
+static void launch_knn_reg(const Grid &g, const QueryView &v, int k, int32_t *oi, float *od, int vec4, cudaStream_t s) {
+    knn_reg_kernel<K><<<nblocks(v.nq, 128), 128, 0, s>>>(g, v, k, oi, od, vec4);
+}
+
+}  // namespace pcc
+
+using namespace pcc;
+
+static int check_common(pcc_index *idx) {
+    if (!idx) return fail(PCC_ERR_INVALID, "idx is NULL");
+    if (!idx->built) return fail(PCC_ERR_STATE, "index not built (call pcc_build first)");
+    PCC_CUDA(cudaSetDevice(idx->device));
+    return PCC_OK;
+}
+
+extern "C" {
+
+int pcc_knn(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int k, int32_t *out_idx, float *out_d2, int *k_eff, int mem, void *stream) {
+    PCC_TRY(check_common(idx));
+    if (k < 1 || k > PCC_MAX_K) return fail(PCC_ERR_INVALID, "k=%d outside 1..%d", k, PCC_MAX_K);
+    cudaStream_t s = (cudaStream_t)stream;
+    Queries qs;
+    PCC_TRY(prepare_queries(idx, q, nq, stride_bytes, mem, s, &qs));
+    if (k_eff) *k_eff = (int)std::min<int64_t>(k, idx->n_indexed);
+    if (qs.rows == 0) return PCC_OK;
+    if (!out_idx || !out_d2) return fail(PCC_ERR_INVALID, "output pointers are NULL");
+    int32_t *oi = out_idx; float *od = out_d2;
+    const size_t cells = (size_t)qs.rows * k;
+    if (mem == PCC_HOST) {
+        PCC_TRY(idx->out_i.reserve(cells * 4)); PCC_TRY(idx->out_f.reserve(cells * 4));
+        oi = idx->out_i.as<int32_t>(); od = idx->out_f.as<float>();
+    }
+    if (qs.self && idx->n_indexed < idx->n_input) {   // rows of skipped (non-finite) points stay empty: (-1, +inf)
+        PCC_CUDA(cudaMemsetAsync(oi, 0xFF, cells * 4, s));
+        fill_f32_kernel<<<nblocks((int64_t)cells, 256), 256, 0, s>>>(od, (int64_t)cells, INFINITY);
+        PCC_LAUNCHED();
+    }
+    const Grid g = idx->grid();
+    const QueryView v = view_of(qs);
+    const int vec4 = ((((uintptr_t)oi) | ((uintptr_t)od)) & 15) == 0 && (k % 4 == 0);
+    KernelTimer timer(idx, s);
+    if (qs.nq > 0) {
+        if (k == 1) launch_knn_reg<1>(g, v, k, oi, od, vec4, s);
+        else if (k <= 2) launch_knn_reg<2>(g, v, k, oi, od, vec4, s);
+        else if (k <= 4) launch_knn_reg<4>(g, v, k, oi, od, vec4, s);
+        else if (k <= 8) launch_knn_reg<8>(g, v, k, oi, od, vec4, s);
+        else if (k <= 16) launch_knn_reg<16>(g, v, k, oi, od, vec4, s);
+        else if (k <= 32) launch_knn_reg<32>(g, v, k, oi, od, vec4, s);
+        else {
+            const int th = heap_threads(k);
+            PCC_TRY(set_heap_smem(knn_heap_kernel));
+            knn_heap_kernel<<<nblocks(v.nq, th), th, (size_t)k * th * sizeof(nkey_t), s>>>(g, v, k, oi, od);
+        }
+        PCC_LAUNCHED();
+        PCC_CUDA(cudaGetLastError());
+    }
+    timer.stop();
+    if (mem == PCC_HOST) {
+        PCC_TRY(copy_out(out_idx, oi, cells * 4, mem, s));
+        PCC_TRY(copy_out(out_d2, od, cells * 4, mem, s));
+        PCC_CUDA(cudaStreamSynchronize(s));
+    }
+    return PCC_OK;
+}
+
+int pcc_knn_mean_dist(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int mean_k, float *out_mean, int mem, void *stream) {
+    PCC_TRY(check_common(idx));
+    if (mean_k < 1 || mean_k + 1 > PCC_MAX_K) return fail(PCC_ERR_INVALID, "mean_k=%d outside 1..%d", mean_k, PCC_MAX_K - 1);
+    cudaStream_t s = (cudaStream_t)stream;
+    Queries qs;
+    PCC_TRY(prepare_queries(idx, q, nq, stride_bytes, mem, s, &qs));
+    if (qs.rows == 0) return PCC_OK;
+    if (!out_mean) return fail(PCC_ERR_INVALID, "output pointer is NULL");
+    float *od = out_mean;
+    if (mem == PCC_HOST) { PCC_TRY(idx->out_f.reserve((size_t)qs.rows * 4)); od = idx->out_f.as<float>(); }
+    if (qs.self && idx->n_indexed < idx->n_input) PCC_CUDA(cudaMemsetAsync(od, 0, (size_t)qs.rows * 4, s));
+    const Grid g = idx->grid();
+    const QueryView v = view_of(qs);
+    const int need = mean_k + 1;
+    KernelTimer timer(idx, s);
+    if (qs.nq > 0) {
+        const unsigned nb = nblocks(v.nq, 128);
+#define PCC_MD(KK)                                                                            \
+    if (need == KK) mean_dist_reg_kernel<KK, true><<<nb, 128, 0, s>>>(g, v, mean_k, od);          \
+    else mean_dist_reg_kernel<KK, false><<<nb, 128, 0, s>>>(g, v, mean_k, od)
+        if (need <= 2) { PCC_MD(2); }
+        else if (need <= 5) { PCC_MD(5); }
+        else if (need <= 9) { PCC_MD(9); }
+        else if (need <= 17) { PCC_MD(17); }
+        else if (need <= 33) { PCC_MD(33); }
+        else if (need <= 51) { PCC_MD(51); }
+#undef PCC_MD
+        else {
+            const int th = heap_threads(need);
+            PCC_TRY(set_heap_smem(mean_dist_heap_kernel));
+            mean_dist_heap_kernel<<<nblocks(v.nq, th), th, (size_t)need * th * sizeof(nkey_t), s>>>(g, v, mean_k, od);
+        }
+        PCC_LAUNCHED();
+        PCC_CUDA(cudaGetLastError());
+    }
+    timer.stop();
+    if (mem == PCC_HOST) { PCC_TRY(copy_out(out_mean, od, (size_t)qs.rows * 4, mem, s)); PCC_CUDA(cudaStreamSynchronize(s)); }
+    return PCC_OK;
+}
+
+int pcc_normals_knn(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int k, const float viewpoint[3], float *out, int mem, void *stream) {
+    PCC_TRY(check_common(idx));
+    if (k < 1 || k > PCC_MAX_K) return fail(PCC_ERR_INVALID, "k=%d outside 1..%d", k, PCC_MAX_K);
+    cudaStream_t s = (cudaStream_t)stream;
+    Queries qs;
+    PCC_TRY(prepare_queries(idx, q, nq, stride_bytes, mem, s, &qs));
+    if (qs.rows == 0) return PCC_OK;
+    if (!out) return fail(PCC_ERR_INVALID, "output pointer is NULL");
+    if (!idx->inv_valid) PCC_TRY(rebuild_inverse(idx, s));
+    float4 *od = (float4 *)out;
+    if (mem == PCC_HOST) { PCC_TRY(idx->out_f.reserve((size_t)qs.rows * 16)); od = idx->out_f.as<float4>(); }
+    if (qs.self && idx->n_indexed < idx->n_input) PCC_CUDA(cudaMemsetAsync(od, 0xFF, (size_t)qs.rows * 16, s));   // 0xFFFFFFFF = NaN
+    const float vx = viewpoint ? viewpoint[0] : 0.f, vy = viewpoint ? viewpoint[1] : 0.f, vz = viewpoint ? viewpoint[2] : 0.f;
+    const Grid g = idx->grid();
+    const QueryView v = view_of(qs);
+    const uint32_t *inv = idx->inv_pos.as<uint32_t>();
+    KernelTimer timer(idx, s);
+    if (qs.nq > 0) {
+        const unsigned nb = nblocks(v.nq, 128);
+        if (k <= 8) normals_knn_reg_kernel<8><<<nb, 128, 0, s>>>(g, v, k, inv, vx, vy, vz, od);
+        else if (k <= 16) normals_knn_reg_kernel<16><<<nb, 128, 0, s>>>(g, v, k, inv, vx, vy, vz, od);
+        else if (k <= 32) normals_knn_reg_kernel<32><<<nb, 128, 0, s>>>(g, v, k, inv, vx, vy, vz, od);
+        else {
+            const int th = heap_threads(k);
+            PCC_TRY(set_heap_smem(normals_knn_heap_kernel));
+            normals_knn_heap_kernel<<<nblocks(v.nq, th), th, (size_t)k * th * sizeof(nkey_t), s>>>(g, v, k, inv, vx, vy, vz, od);
+        }
+        PCC_LAUNCHED();
+        PCC_CUDA(cudaGetLastError());
+    }
+    timer.stop();
+    if (mem == PCC_HOST) { PCC_TRY(copy_out(out, od, (size_t)qs.rows * 16, mem, s)); PCC_CUDA(cudaStreamSynchronize(s)); }
+    return PCC_OK;
+}
+
+// src working copy lives in idx->stage4-independent buffer `parent` is reserved for clustering; ICP uses qbuf-sized `keys64b`
+int pcc_icp_step(pcc_index *idx, void *src_inout, int64_t ns, int stride_bytes, const float *T_apply, double sums[16], int64_t *count,
+                 int32_t *corr_idx, float *corr_d2, int mem, void *stream) {
+    PCC_TRY(check_common(idx));
+    if (ns < 0 || stride_bytes < 12 || (stride_bytes & 3)) return fail(PCC_ERR_INVALID, "bad source cloud (ns=%lld stride=%d)", (long long)ns, stride_bytes);
+    if (!sums || !count) return fail(PCC_ERR_INVALID, "sums / count are NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int i = 0; i < 16; ++i) sums[i] = 0;
+    *count = 0;
+    if (ns == 0) return PCC_OK;
+    // working float4 copy + cell-sorted processing order of the (untransformed) source
+    Queries qs;
+    PCC_TRY(prepare_queries(idx, src_inout, ns, stride_bytes, mem, s, &qs));
+    float4 *work = idx->qbuf.as<float4>();
+    Mat34 T; int apply = 0;
+    if (T_apply) { memcpy(T.m, T_apply, sizeof(T.m)); apply = 1; } else memset(&T, 0, sizeof(T));
+    const unsigned nb = nblocks(ns, kIcpThreads);
+    PCC_TRY(idx->keys64b.reserve(((size_t)nb * 17 + 32) * sizeof(double)));
+    double *partials = idx->keys64b.as<double>();
+    double *d_out = partials + (size_t)nb * 17;
+    int32_t *ci = corr_idx; float *cd = corr_d2;
+    if (mem == PCC_HOST) {
+        if (corr_idx) { PCC_TRY(idx->out_i.reserve((size_t)ns * 4)); ci = idx->out_i.as<int32_t>(); }
+        if (corr_d2) { PCC_TRY(idx->out_f.reserve((size_t)ns * 4)); cd = idx->out_f.as<float>(); }
+    }
+    KernelTimer timer(idx, s);
+    icp_step_kernel<<<nb, kIcpThreads, 0, s>>>(idx->grid(), work, qs.order, ns, T, apply, partials, ci, cd);
+    PCC_LAUNCHED();
+    icp_reduce_kernel<<<17, 256, 0, s>>>(partials, nb, d_out);
+    PCC_LAUNCHED();
+    PCC_CUDA(cudaGetLastError());
+    timer.stop();
+    double *h = (double *)idx->h_pinned;
+    PCC_CUDA(cudaMemcpyAsync(h, d_out, 17 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (apply) {   // hand the moved points back in the caller's layout
+        if (mem == PCC_DEVICE) {
+            icp_store_kernel<<<nblocks(ns, 256), 256, 0, s>>>(work, ns, (uint8_t *)src_inout, stride_bytes);
+            PCC_LAUNCHED();
+        } else {
+            icp_store_kernel<<<nblocks(ns, 256), 256, 0, s>>>(work, ns, idx->raw.as<uint8_t>(), stride_bytes);
+            PCC_LAUNCHED();
+            PCC_CUDA(cudaMemcpyAsync(src_inout, idx->raw.p, (size_t)ns * stride_bytes, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    if (mem == PCC_HOST) {
+        if (corr_idx) PCC_TRY(copy_out(corr_idx, ci, (size_t)ns * 4, mem, s));
+        if (corr_d2) PCC_TRY(copy_out(corr_d2, cd, (size_t)ns * 4, mem, s));
+    }
+    PCC_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < 16; ++i) sums[i] = h[i];
+    *count = (int64_t)llround(h[16]);
+    return PCC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,406 @@
+// pcc_radius.cu -- batched fixed-radius queries (CSR output) and the consumers built on them.
+//
+// Replaces: a3 Search::radiusSearch batched, a4 NormalEstimation with setRadiusSearch,
+// a7 EuclideanClusterExtraction (GPU union-find over the radius graph), a9 the SIFT keypoint snap loop.
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "pcc_internal.h"
+
+namespace pcc {
+
+struct QueryView { const float4 *q; const uint32_t *order; int64_t nq; bool self; };
+static inline QueryView view_of(const Queries &q) { return QueryView{q.q, q.order, q.nq, q.self}; }
+static inline unsigned nblocks(int64_t n, int threads) { return (unsigned)std::max<int64_t>(1, (n + threads - 1) / threads); }
+
+__device__ __forceinline__ bool load_query(const Grid &g, const QueryView &v, int64_t t, float &x, float &y, float &z, int64_t &row) {
+    if (t >= v.nq) return false;
+    if (v.self) { float4 p = __ldg(g.pts + t); x = p.x; y = p.y; z = p.z; row = __float_as_int(p.w); return true; }
+    uint32_t qi = v.order ? __ldg(v.order + t) : (uint32_t)t;
+    float4 p = __ldg(v.q + qi); x = p.x; y = p.y; z = p.z; row = qi;
+    return finite3(x, y, z) && g.n > 0;
+}
+
+// visit every indexed point with d2 < r2 (strict, KdTreeFLANN::radiusSearch [up]); R0 = ceil(r / cell)
+template <class F>
+__device__ __forceinline__ void radius_visit(const Grid &g, float x, float y, float z, float r2, int R0, F &&f) {
+    const QueryCell c = locate(g, x, y, z);
+    int Rin = -1, R = R0;
+    for (;;) {
+        scan_shell(g, c, Rin, R, [&](uint32_t pos, float4 p) { const float d2 = dist2(x, y, z, p.x, p.y, p.z); if (d2 < r2) f(pos, p, d2); });
+        if (covered_d2(g, c, R) >= r2) break;
+        Rin = R; ++R;
+    }
+}
+
+__global__ void __launch_bounds__(128) radius_count_kernel(Grid g, QueryView v, float r2, int R0, unsigned max_nn, int64_t *__restrict__ counts) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float x, y, z; int64_t row;
+    if (!load_query(g, v, t, x, y, z, row)) return;      // counts are pre-zeroed
+    unsigned n = 0;
+    radius_visit(g, x, y, z, r2, R0, [&](uint32_t, float4, float) { ++n; });
+    if (max_nn && n > max_nn) n = max_nn;
+    counts[row] = n;
+}
+// rows as packed (d2, idx) keys in visit order
+__global__ void __launch_bounds__(128) radius_fill_kernel(Grid g, QueryView v, float r2, int R0, const int64_t *__restrict__ offsets, nkey_t *__restrict__ keys) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float x, y, z; int64_t row;
+    if (!load_query(g, v, t, x, y, z, row)) return;
+    nkey_t *o = keys + offsets[row];
+    radius_visit(g, x, y, z, r2, R0, [&](uint32_t, float4 p, float d2) { *o++ = make_key(d2, __float_as_uint(p.w)); });
+}
+// max_nn-capped rows: keep the max_nn smallest keys in a shared-memory heap, emit them sorted
+__global__ void radius_capped_kernel(Grid g, QueryView v, float r2, int R0, int max_nn, const int64_t *__restrict__ offsets, nkey_t *__restrict__ keys) {
+    extern __shared__ nkey_t smem_keys[];
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float x, y, z; int64_t row;
+    if (!load_query(g, v, t, x, y, z, row)) return;
+    HeapList list; list.init(smem_keys + threadIdx.x, blockDim.x, max_nn);
+    radius_visit(g, x, y, z, r2, R0, [&](uint32_t, float4 p, float d2) { list.offer(make_key(d2, __float_as_uint(p.w))); });
+    list.finish();
+    nkey_t *o = keys + offsets[row];
+    for (int j = 0; j < list.cnt; ++j) o[j] = list.at(j);
+}
+__global__ void unpack_kernel(const nkey_t *__restrict__ keys, int64_t n, int32_t *__restrict__ idx, float *__restrict__ d2) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    nkey_t k = keys[i];
+    idx[i] = (int32_t)(uint32_t)k; d2[i] = __uint_as_float((uint32_t)(k >> 32));
+}
+
+// NormalEstimation(radius): accumulate the (d2, idx)-sorted row in order, exactly like the kNN variant
+__global__ void __launch_bounds__(128) normals_rows_kernel(Grid g, QueryView v, const int64_t *__restrict__ offsets, const nkey_t *__restrict__ keys,
+                                                           const uint32_t *__restrict__ inv_pos, float vx, float vy, float vz, float4 *__restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= v.nq) return;
+    float x, y, z; int64_t row;
+    if (v.self) { float4 p = __ldg(g.pts + t); x = p.x; y = p.y; z = p.z; row = __float_as_int(p.w); }
+    else { uint32_t qi = v.order ? __ldg(v.order + t) : (uint32_t)t; float4 p = __ldg(v.q + qi); x = p.x; y = p.y; z = p.z; row = qi; }
+    const int64_t b = offsets[row], e = offsets[row + 1];
+    float a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t j = b; j < e; ++j) { float4 p = __ldg(g.pts + __ldg(inv_pos + (uint32_t)keys[j])); accu_add(a, p.x, p.y, p.z); }
+    out[row] = normal_from_accu(a, (int)min((int64_t)INT_MAX, e - b), x, y, z, vx, vy, vz);
+}
+
+// SIFT keypoint snap: lowest original index with sqrt(double(dx)^2 + double(dy)^2 + double(dz)^2) < thr
+__global__ void __launch_bounds__(128) first_within_kernel(Grid g, QueryView v, double thr, float r2_cover, int R0, int32_t *__restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= v.nq) return;
+    const uint32_t qi = v.order ? __ldg(v.order + t) : (uint32_t)t;
+    const float4 q = __ldg(v.q + qi);
+    int32_t best = INT_MAX;
+    if (finite3(q.x, q.y, q.z) && g.n > 0) {
+        const QueryCell c = locate(g, q.x, q.y, q.z);
+        int Rin = -1, R = R0;
+        for (;;) {
+            scan_shell(g, c, Rin, R, [&](uint32_t, float4 p) {
+                const double dx = (double)(q.x - p.x), dy = (double)(q.y - p.y), dz = (double)(q.z - p.z);
+                if (sqrt(dx * dx + dy * dy + dz * dz) < thr) best = min(best, __float_as_int(p.w));
+            });
+            if (covered_d2(g, c, R) >= r2_cover) break;
+            Rin = R; ++R;
+        }
+    }
+    out[qi] = best == INT_MAX ? -1 : best;
+}
+
+// ---- EuclideanClusterExtraction: lock-free union-find over sorted positions ----
+// Loads bypass L1 (__ldcg) so a root that another SM has just hooked is seen in L2; a stale value is still
+// an ancestor in the same set, so following it is safe, and the CAS below is the only way a root changes.
+__device__ __forceinline__ uint32_t uf_find(uint32_t *parent, uint32_t x) {
+    uint32_t p = __ldcg(parent + x);
+    while (p != x) { uint32_t gp = __ldcg(parent + p); if (gp != p) parent[x] = gp; x = p; p = gp; }   // path halving
+    return x;
+}
+__device__ __forceinline__ void uf_union(uint32_t *parent, uint32_t a, uint32_t b) {
+    for (;;) {
+        a = uf_find(parent, a); b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { uint32_t t = a; a = b; b = t; }      // hook the larger root under the smaller
+        const uint32_t old = atomicCAS(parent + a, a, b);
+        if (old == a) return;
+        a = old;                                            // lost the race: continue from the true parent
+    }
+}
+__global__ void iota_kernel(uint32_t *p, int64_t n) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = (uint32_t)i; }
+__global__ void __launch_bounds__(128) ece_link_kernel(Grid g, float r2, int R0, uint32_t *__restrict__ parent) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.n) return;
+    const float4 q = __ldg(g.pts + t);
+    radius_visit(g, q.x, q.y, q.z, r2, R0, [&](uint32_t pos, float4, float) { if (pos < (uint32_t)t) uf_union(parent, (uint32_t)t, pos); });
+}
+__global__ void ece_flatten_kernel(Grid g, uint32_t *__restrict__ parent, uint32_t *__restrict__ size, uint32_t *__restrict__ min_orig) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.n) return;
+    const uint32_t r = uf_find(parent, (uint32_t)t);
+    parent[t] = r;      // safe: r is a root, roots never change in this kernel
+    atomicAdd(size + r, 1u);
+    atomicMin(min_orig + r, (uint32_t)__float_as_int(__ldg(g.pts + t).w));
+}
+// kept roots -> (sort key, root) list; key orders by size descending then smallest member index
+__global__ void ece_select_kernel(uint32_t n, const uint32_t *__restrict__ parent, const uint32_t *__restrict__ size, const uint32_t *__restrict__ min_orig,
+                                  uint32_t min_size, uint32_t max_size, nkey_t *__restrict__ keys, uint32_t *__restrict__ roots, unsigned long long *__restrict__ n_kept) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n || parent[t] != (uint32_t)t) return;
+    const uint32_t s = size[t];
+    if (s < min_size || s > max_size) return;
+    const unsigned long long slot = atomicAdd(n_kept, 1ull);
+    keys[slot] = ((nkey_t)(0xFFFFFFFFu - s) << 32) | min_orig[t];
+    roots[slot] = (uint32_t)t;
+}
+__global__ void ece_rank_kernel(const nkey_t *__restrict__ keys_sorted, const uint32_t *__restrict__ roots_sorted, int64_t n_kept, uint32_t *__restrict__ rank_of_root, int64_t *__restrict__ sizes, int64_t sizes_cap) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_kept) return;
+    rank_of_root[roots_sorted[i]] = (uint32_t)i;
+    if (sizes && i < sizes_cap) sizes[i] = (int64_t)(0xFFFFFFFFu - (uint32_t)(keys_sorted[i] >> 32));
+}
+__global__ void ece_label_kernel(Grid g, const uint32_t *__restrict__ parent, const uint32_t *__restrict__ rank_of_root, int32_t *__restrict__ labels) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.n) return;
+    labels[__float_as_int(__ldg(g.pts + t).w)] = (int32_t)rank_of_root[parent[t]];
+}
+__global__ void fill_u32_kernel(uint32_t *p, int64_t n, uint32_t v) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+
+static int heap_threads(int k) {
+    int t = (int)((96 * 1024) / ((size_t)k * sizeof(nkey_t)));
+    t = std::min(128, (t / 32) * 32);
+    return std::max(32, t);
+}
+static inline int ring0(const pcc_index *idx, double radius) { return std::max(1, (int)std::ceil(radius / (double)idx->gh.cell)); }
+
+// shared by pcc_radius_count and the internal consumers: counts (device, zeroed, rows+1) -> inclusive CSR offsets
+static int radius_offsets(pcc_index *idx, const Queries &qs, double radius, unsigned max_nn, int64_t *d_offsets, cudaStream_t s) {
+    const float r2 = (float)(radius * radius);
+    PCC_CUDA(cudaMemsetAsync(d_offsets, 0, (size_t)(qs.rows + 1) * sizeof(int64_t), s));
+    if (qs.nq > 0) {
+        radius_count_kernel<<<nblocks(qs.nq, 128), 128, 0, s>>>(idx->grid(), view_of(qs), r2, ring0(idx, radius), max_nn, d_offsets);
+        PCC_LAUNCHED();
+        PCC_CUDA(cudaGetLastError());
+    }
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_offsets, d_offsets, (int)(qs.rows + 1), s);
+    PCC_TRY(idx->cub_tmp.reserve(tmp));
+    PCC_CUDA(cub::DeviceScan::ExclusiveSum(idx->cub_tmp.p, tmp, d_offsets, d_offsets, (int)(qs.rows + 1), s));
+    g_launches += 2;
+    return PCC_OK;
+}
+// rows as packed keys into idx->keys64 (sorted in place when requested); total = offsets[rows]
+static int radius_rows(pcc_index *idx, const Queries &qs, double radius, unsigned max_nn, int sorted, const int64_t *d_offsets, int64_t total, nkey_t **keys_out, cudaStream_t s) {
+    const float r2 = (float)(radius * radius);
+    PCC_TRY(idx->keys64.reserve((size_t)std::max<int64_t>(total, 1) * sizeof(nkey_t)));
+    nkey_t *keys = idx->keys64.as<nkey_t>();
+    *keys_out = keys;
+    if (qs.nq == 0 || total == 0) return PCC_OK;
+    const bool capped = max_nn != 0 && (int64_t)max_nn < idx->n_indexed;
+    if (capped) {
+        if (max_nn > PCC_MAX_K) return fail(PCC_ERR_INVALID, "max_nn=%u above %d is only supported when it is >= the indexed point count", max_nn, PCC_MAX_K);
+        const int th = heap_threads((int)max_nn);
+        static bool attr = false;
+        if (!attr) { PCC_CUDA(cudaFuncSetAttribute(radius_capped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+        radius_capped_kernel<<<nblocks(qs.nq, th), th, (size_t)max_nn * th * sizeof(nkey_t), s>>>(idx->grid(), view_of(qs), r2, ring0(idx, radius), (int)max_nn, d_offsets, keys);
+        PCC_LAUNCHED();
+        PCC_CUDA(cudaGetLastError());
+        return PCC_OK;   // already sorted
+    }
+    radius_fill_kernel<<<nblocks(qs.nq, 128), 128, 0, s>>>(idx->grid(), view_of(qs), r2, ring0(idx, radius), d_offsets, keys);
+    PCC_LAUNCHED();
+    PCC_CUDA(cudaGetLastError());
+    if (sorted) {
+        if (total >= (1ll << 31)) return fail(PCC_ERR_INVALID, "radius result of %lld neighbours exceeds the segmented-sort limit", (long long)total);
+        PCC_TRY(idx->keys64b.reserve((size_t)total * sizeof(nkey_t)));
+        cub::DoubleBuffer<nkey_t> db(keys, idx->keys64b.as<nkey_t>());
+        size_t tmp = 0;
+        cub::DeviceSegmentedSort::SortKeys(nullptr, tmp, db, (int)total, (int)qs.rows, d_offsets, d_offsets + 1, s);
+        PCC_TRY(idx->cub_tmp.reserve(tmp));
+        PCC_CUDA(cub::DeviceSegmentedSort::SortKeys(idx->cub_tmp.p, tmp, db, (int)total, (int)qs.rows, d_offsets, d_offsets + 1, s));
+        g_launches += 3;
+        *keys_out = db.Current();
+    }
+    return PCC_OK;
+}
+
+}  // namespace pcc
+
+using namespace pcc;
+
+static int check_common(pcc_index *idx) {
+    if (!idx) return fail(PCC_ERR_INVALID, "idx is NULL");
+    if (!idx->built) return fail(PCC_ERR_STATE, "index not built (call pcc_build first)");
+    PCC_CUDA(cudaSetDevice(idx->device));
+    return PCC_OK;
+}
+
+extern "C" {
+
+int pcc_radius_count(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, double radius, unsigned max_nn, int64_t *offsets, int64_t *total, int mem, void *stream) {
+    PCC_TRY(check_common(idx));
+    if (!(radius >= 0) || !offsets) return fail(PCC_ERR_INVALID, "bad radius / offsets");
+    cudaStream_t s = (cudaStream_t)stream;
+    Queries qs;
+    PCC_TRY(prepare_queries(idx, q, nq, stride_bytes, mem, s, &qs));
+    int64_t *d_off = offsets;
+    if (mem == PCC_HOST) { PCC_TRY(idx->out_l.reserve((size_t)(qs.rows + 1) * 8)); d_off = idx->out_l.as<int64_t>(); }
+    KernelTimer timer(idx, s);
+    PCC_TRY(radius_offsets(idx, qs, radius, max_nn, d_off, s));
+    timer.stop();
+    int64_t *h = (int64_t *)idx->h_pinned;
+    PCC_CUDA(cudaMemcpyAsync(h, d_off + qs.rows, 8, cudaMemcpyDeviceToHost, s));
+    if (mem == PCC_HOST) PCC_TRY(copy_out(offsets, d_off, (size_t)(qs.rows + 1) * 8, mem, s));
+    PCC_CUDA(cudaStreamSynchronize(s));
+    if (total) *total = h[0];
+    return PCC_OK;
+}
+
+int pcc_radius_fill(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, double radius, unsigned max_nn, int sorted, const int64_t *offsets,
+                    int32_t *out_idx, float *out_d2, int mem, void *stream) {
+    PCC_TRY(check_common(idx));
+    if (!(radius >= 0) || !offsets) return fail(PCC_ERR_INVALID, "bad radius / offsets");
+    cudaStream_t s = (cudaStream_t)stream;
+    Queries qs;
+    PCC_TRY(prepare_queries(idx, q, nq, stride_bytes, mem, s, &qs));
+    const int64_t *d_off = offsets;
+    int64_t total = 0;
+    if (mem == PCC_HOST) {
+        PCC_TRY(idx->out_l.reserve((size_t)(qs.rows + 1) * 8));
+        PCC_CUDA(cudaMemcpyAsync(idx->out_l.p, offsets, (size_t)(qs.rows + 1) * 8, cudaMemcpyHostToDevice, s));
+        d_off = idx->out_l.as<int64_t>();
+        total = offsets[qs.rows];
+    } else {
+        int64_t *h = (int64_t *)idx->h_pinned;
+        PCC_CUDA(cudaMemcpyAsync(h, offsets + qs.rows, 8, cudaMemcpyDeviceToHost, s));
+        PCC_CUDA(cudaStreamSynchronize(s));
+        total = h[0];
+    }
+    if (total == 0) return PCC_OK;
+    if (!out_idx || !out_d2) return fail(PCC_ERR_INVALID, "output pointers are NULL");
+    nkey_t *keys = nullptr;
+    KernelTimer timer(idx, s);
+    PCC_TRY(radius_rows(idx, qs, radius, max_nn, sorted, d_off, total, &keys, s));
+    int32_t *oi = out_idx; float *od = out_d2;
+    if (mem == PCC_HOST) { PCC_TRY(idx->out_i.reserve((size_t)total * 4)); PCC_TRY(idx->out_f.reserve((size_t)total * 4)); oi = idx->out_i.as<int32_t>(); od = idx->out_f.as<float>(); }
+    unpack_kernel<<<nblocks(total, 256), 256, 0, s>>>(keys, total, oi, od);
+    PCC_LAUNCHED();
+    PCC_CUDA(cudaGetLastError());
+    timer.stop();
+    if (mem == PCC_HOST) {
+        PCC_TRY(copy_out(out_idx, oi, (size_t)total * 4, mem, s));
+        PCC_TRY(copy_out(out_d2, od, (size_t)total * 4, mem, s));
+        PCC_CUDA(cudaStreamSynchronize(s));
+    }
+    return PCC_OK;
+}
+
+int pcc_normals_radius(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, double radius, const float viewpoint[3], float *out, int mem, void *stream) {
+    PCC_TRY(check_common(idx));
+    if (!(radius >= 0)) return fail(PCC_ERR_INVALID, "bad radius");
+    cudaStream_t s = (cudaStream_t)stream;
+    Queries qs;
+    PCC_TRY(prepare_queries(idx, q, nq, stride_bytes, mem, s, &qs));
+    if (qs.rows == 0) return PCC_OK;
+    if (!out) return fail(PCC_ERR_INVALID, "output pointer is NULL");
+    if (!idx->inv_valid) PCC_TRY(rebuild_inverse(idx, s));
+    PCC_TRY(idx->out_l.reserve((size_t)(qs.rows + 1) * 8));
+    int64_t *d_off = idx->out_l.as<int64_t>();
+    KernelTimer timer(idx, s);
+    PCC_TRY(radius_offsets(idx, qs, radius, 0, d_off, s));
+    int64_t *h = (int64_t *)idx->h_pinned;
+    PCC_CUDA(cudaMemcpyAsync(h, d_off + qs.rows, 8, cudaMemcpyDeviceToHost, s));
+    PCC_CUDA(cudaStreamSynchronize(s));
+    const int64_t total = h[0];
+    nkey_t *keys = nullptr;
+    PCC_TRY(radius_rows(idx, qs, radius, 0, 1, d_off, total, &keys, s));
+    float4 *od = (float4 *)out;
+    if (mem == PCC_HOST) { PCC_TRY(idx->out_f.reserve((size_t)qs.rows * 16)); od = idx->out_f.as<float4>(); }
+    if (qs.self && idx->n_indexed < idx->n_input) PCC_CUDA(cudaMemsetAsync(od, 0xFF, (size_t)qs.rows * 16, s));
+    const float vx = viewpoint ? viewpoint[0] : 0.f, vy = viewpoint ? viewpoint[1] : 0.f, vz = viewpoint ? viewpoint[2] : 0.f;
+    if (qs.nq > 0) {
+        normals_rows_kernel<<<nblocks(qs.nq, 128), 128, 0, s>>>(idx->grid(), view_of(qs), d_off, keys, idx->inv_pos.as<uint32_t>(), vx, vy, vz, od);
+        PCC_LAUNCHED();
+        PCC_CUDA(cudaGetLastError());
+    }
+    timer.stop();
+    if (mem == PCC_HOST) { PCC_TRY(copy_out(out, od, (size_t)qs.rows * 16, mem, s)); PCC_CUDA(cudaStreamSynchronize(s)); }
+    return PCC_OK;
+}
+
+int pcc_first_within(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, double thr, int32_t *out, int mem, void *stream) {
+    PCC_TRY(check_common(idx));
+    if (!(thr >= 0) || !q) return fail(PCC_ERR_INVALID, "bad threshold / queries");
+    cudaStream_t s = (cudaStream_t)stream;
+    Queries qs;
+    PCC_TRY(prepare_queries(idx, q, nq, stride_bytes, mem, s, &qs));
+    if (qs.rows == 0) return PCC_OK;
+    int32_t *oi = out;
+    if (mem == PCC_HOST) { PCC_TRY(idx->out_i.reserve((size_t)nq * 4)); oi = idx->out_i.as<int32_t>(); }
+    const float r2_cover = (float)(thr * thr * (1.0 + 1e-5));
+    first_within_kernel<<<nblocks(nq, 128), 128, 0, s>>>(idx->grid(), view_of(qs), thr, r2_cover, ring0(idx, thr), oi);
+    PCC_LAUNCHED();
+    PCC_CUDA(cudaGetLastError());
+    if (mem == PCC_HOST) { PCC_TRY(copy_out(out, oi, (size_t)nq * 4, mem, s)); PCC_CUDA(cudaStreamSynchronize(s)); }
+    return PCC_OK;
+}
+
+int pcc_euclidean_labels(pcc_index *idx, double tolerance, int64_t min_size, int64_t max_size, int32_t *labels, int64_t *n_clusters, int64_t *sizes,
+                         int64_t sizes_cap, int mem, void *stream) {
+    PCC_TRY(check_common(idx));
+    if (!(tolerance >= 0) || !labels || !n_clusters) return fail(PCC_ERR_INVALID, "bad tolerance / outputs");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n = idx->n_indexed, rows = idx->n_input;
+    *n_clusters = 0;
+    if (rows == 0) return PCC_OK;
+    int32_t *d_labels = labels;
+    if (mem == PCC_HOST) { PCC_TRY(idx->out_i.reserve((size_t)rows * 4)); d_labels = idx->out_i.as<int32_t>(); }
+    PCC_CUDA(cudaMemsetAsync(d_labels, 0xFF, (size_t)rows * 4, s));
+    int64_t kept = 0;
+    int64_t *d_sizes = sizes;
+    if (n > 0) {
+        const float r2 = (float)(tolerance * tolerance);
+        const Grid g = idx->grid();
+        // parent | size | min_orig | rank_of_root | roots | roots_sorted : 6 x uint32[n]; keys | keys_sorted : 2 x u64[n]
+        PCC_TRY(idx->parent.reserve((size_t)n * 4 * 6));
+        PCC_TRY(idx->keys64.reserve((size_t)n * 8 + 64)); PCC_TRY(idx->keys64b.reserve((size_t)n * 8));
+        uint32_t *parent = idx->parent.as<uint32_t>(), *size = parent + n, *min_orig = size + n, *rank_of_root = min_orig + n, *roots = rank_of_root + n, *roots_sorted = roots + n;
+        nkey_t *keys = idx->keys64.as<nkey_t>(), *keys_sorted = idx->keys64b.as<nkey_t>();
+        unsigned long long *d_kept = (unsigned long long *)(keys + n);
+        const unsigned nb = nblocks(n, 128), nb256 = nblocks(n, 256);
+        KernelTimer timer(idx, s);
+        iota_kernel<<<nb256, 256, 0, s>>>(parent, n); PCC_LAUNCHED();
+        PCC_CUDA(cudaMemsetAsync(size, 0, (size_t)n * 4, s));
+        PCC_CUDA(cudaMemsetAsync(min_orig, 0xFF, (size_t)n * 4, s));
+        PCC_CUDA(cudaMemsetAsync(rank_of_root, 0xFF, (size_t)n * 4, s));
+        PCC_CUDA(cudaMemsetAsync(d_kept, 0, 8, s));
+        ece_link_kernel<<<nb, 128, 0, s>>>(g, r2, ring0(idx, tolerance), parent); PCC_LAUNCHED();
+        ece_flatten_kernel<<<nb256, 256, 0, s>>>(g, parent, size, min_orig); PCC_LAUNCHED();
+        const uint32_t mn = (uint32_t)std::min<int64_t>(std::max<int64_t>(min_size, 0), 0xFFFFFFFFll), mxs = (uint32_t)std::min<int64_t>(std::max<int64_t>(max_size, 0), 0xFFFFFFFFll);
+        ece_select_kernel<<<nb256, 256, 0, s>>>((uint32_t)n, parent, size, min_orig, mn, mxs, keys, roots, d_kept); PCC_LAUNCHED();
+        PCC_CUDA(cudaGetLastError());
+        unsigned long long *h = (unsigned long long *)idx->h_pinned;
+        PCC_CUDA(cudaMemcpyAsync(h, d_kept, 8, cudaMemcpyDeviceToHost, s));
+        PCC_CUDA(cudaStreamSynchronize(s));
+        kept = (int64_t)h[0];
+        if (kept > 0) {
+            size_t tmp = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys, keys_sorted, roots, roots_sorted, (int)kept, 0, 64, s);
+            PCC_TRY(idx->cub_tmp.reserve(tmp));
+            PCC_CUDA(cub::DeviceRadixSort::SortPairs(idx->cub_tmp.p, tmp, keys, keys_sorted, roots, roots_sorted, (int)kept, 0, 64, s));
+            g_launches += 8;
+            if (sizes && mem == PCC_HOST) { PCC_TRY(idx->out_l.reserve((size_t)std::min(kept, sizes_cap) * 8 + 8)); d_sizes = idx->out_l.as<int64_t>(); }
+            ece_rank_kernel<<<nblocks(kept, 256), 256, 0, s>>>(keys_sorted, roots_sorted, kept, rank_of_root, d_sizes, sizes_cap); PCC_LAUNCHED();
+        }
+        ece_label_kernel<<<nb256, 256, 0, s>>>(g, parent, rank_of_root, d_labels); PCC_LAUNCHED();
+        PCC_CUDA(cudaGetLastError());
+        timer.stop();
+    }
+    if (mem == PCC_HOST) {
+        PCC_TRY(copy_out(labels, d_labels, (size_t)rows * 4, mem, s));
+        if (sizes && kept > 0) PCC_TRY(copy_out(sizes, d_sizes, (size_t)std::min(kept, sizes_cap) * 8, mem, s));
+    }
+    PCC_CUDA(cudaStreamSynchronize(s));
+    *n_clusters = kept;
+    return PCC_OK;
+}
+
+}  // extern "C"

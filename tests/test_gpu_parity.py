@@ -1,0 +1,296 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs and against the committed golden vectors.  Bar: bit-exact indices / fp32 squared distances / labels;
+1e-5 relative (stated per test) for floating-point reductions.  Run on the B200 box with `-m gpu`."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import bits
+from pointcloudcomparator_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def GS():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from pointcloudcomparator_b200.search import GridSearch
+    return GridSearch
+
+
+def assert_knn_equal(gi, gd, oi, od):
+    assert np.array_equal(gi, oi), f"index mismatch in {np.argwhere(gi != oi)[:5].tolist()}"
+    assert np.array_equal(bits(gd), bits(od))
+
+
+# ---------------------------------------------------------------- kNN
+def test_golden_knn_and_radius(GS, golden):
+    s = GS().setInputCloud(golden["ref"])
+    for k in (1, 16, 50):
+        gi, gd, keff = s.nearestKSearch(golden["qry"], k)
+        assert keff == k
+        assert_knn_equal(gi, gd, golden[f"knn{k}_idx"], golden[f"knn{k}_d2"])
+    off, idx, d2 = s.radiusSearch(golden["qry"], float(golden["radius"]))
+    assert np.array_equal(off, golden["rad_off"]) and np.array_equal(idx, golden["rad_idx"]) and np.array_equal(bits(d2), bits(golden["rad_d2"]))
+    u = GS().setInputCloud(golden["uref"])
+    gi, gd, _ = u.nearestKSearch(golden["uqry"], 16)
+    assert_knn_equal(gi, gd, golden["uknn16_idx"], golden["uknn16_d2"])
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 8, 16, 17, 32, 33, 50, 51, 100, 128])
+def test_knn_room_vs_oracle(GS, k):
+    ref = synth.room(100000, 1001)
+    qry = synth.noisy_copy(ref, 1002, 0.002)[:20000]
+    s = GS().setInputCloud(ref, k_hint=k)
+    gi, gd, keff = s.nearestKSearch(qry, k)
+    oi, od, okeff = oracle.KdTree(ref).knn(qry, k)
+    assert keff == okeff == k
+    assert_knn_equal(gi, gd, oi, od)
+
+
+@pytest.mark.parametrize("k", [1, 16, 50])
+def test_knn_self_query_all_points(GS, k):
+    ref = synth.room(60000, 2001, stride4=True)
+    s = GS().setInputCloud(ref, k_hint=k)
+    gi, gd, _ = s.nearestKSearch(None, k)                      # RegionGrowing::findPointNeighbours shape: N x k table
+    oi, od, _ = oracle.KdTree(ref).knn(ref, k)
+    assert_knn_equal(gi, gd, oi, od)
+    assert (gi[:, 0] == np.arange(ref.shape[0])).all()         # tie-free cloud: nearest is the point itself
+
+
+def test_knn_uniform_volume_and_mismatched_k_hint(GS):
+    ref = synth.uniform(200000, 5001, extent=4.0)
+    qry = synth.sweep_queries(ref, 30000, seed=5002, sigma=0.05)
+    s = GS().setInputCloud(ref, k_hint=4)                     # grid tuned for k=4, queried at k=32 -> ring expansion
+    for k in (1, 32):
+        gi, gd, _ = s.nearestKSearch(qry, k)
+        oi, od, _ = oracle.KdTree(ref).knn(qry, k)
+        assert_knn_equal(gi, gd, oi, od)
+
+
+def test_knn_lattice_ties_everywhere(GS):
+    g = np.arange(16, dtype=np.float32) * 0.25
+    ref = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    ref = ref[np.random.default_rng(0).permutation(len(ref))]
+    s = GS().setInputCloud(ref)
+    for k in (1, 7, 8, 27, 50):
+        gi, gd, _ = s.nearestKSearch(ref, k)
+        oi, od, _ = oracle.brute_knn(ref, ref, k)
+        assert_knn_equal(gi, gd, oi, od)
+
+
+def test_knn_duplicates_nan_rows_k_gt_n(GS):
+    ref = np.array([[0, 0, 0], [np.nan, 0, 0], [1, 0, 0], [1, 0, 0], [0, 2, 0], [np.inf, 1, 1]], np.float32)
+    qry = np.array([[0.9, 0, 0], [np.nan, 0, 0], [100, -50, 3]], np.float32)
+    s = GS().setInputCloud(ref)
+    assert s.size == 4
+    gi, gd, keff = s.nearestKSearch(qry, 6)
+    oi, od, okeff = oracle.brute_knn(ref, qry, 6)
+    assert keff == okeff == 4
+    assert_knn_equal(gi, gd, oi, od)
+    assert gi[0].tolist() == [2, 3, 0, 4, -1, -1] and (gi[1] == -1).all()
+    gi, gd, _ = s.nearestKSearch(None, 3)                       # self query: skipped rows stay empty
+    oi, od, _ = oracle.brute_knn(ref, ref, 3)
+    assert_knn_equal(gi, gd, oi, od)
+
+
+def test_knn_outliers_negative_coords_cell_faces(GS):
+    rng = np.random.default_rng(3)
+    ref = np.concatenate([rng.normal(0, 0.05, (20000, 3)), rng.normal(0, 0.05, (20000, 3)) + [3, -2, 1], [[40, 40, 40], [-35, 0, 7]]]).astype(np.float32)
+    s = GS().setInputCloud(ref, cell_hint=0.0625)
+    cell = np.float32(0.0625)
+    origin = ref.min(0)
+    on_faces = (origin + cell * rng.integers(0, 40, (2000, 3)).astype(np.float32)).astype(np.float32)    # exactly on cell faces
+    far = rng.uniform(-60, 60, (500, 3)).astype(np.float32)                                              # far outside the bbox
+    qry = np.concatenate([on_faces, far, ref[::97]])
+    for k in (1, 16):
+        gi, gd, _ = s.nearestKSearch(qry, k)
+        oi, od, _ = oracle.KdTree(ref).knn(qry, k)
+        assert_knn_equal(gi, gd, oi, od)
+
+
+def test_knn_indices_subset_and_stride32(GS):
+    pts = np.zeros((30000, 8), np.float32)
+    pts[:, :3] = synth.room(30000, 77)
+    pts[:, 3] = 1.0
+    sub = np.random.default_rng(1).choice(30000, 9000, replace=False).astype(np.int32)
+    s = GS().setInputCloud(pts, indices=sub)
+    qry = pts[:4000]
+    gi, gd, _ = s.nearestKSearch(qry, 8)
+    oi, od, _ = oracle.brute_knn(pts[sub], qry, 8)
+    assert_knn_equal(gi, gd, sub[oi], od)                       # returned indices address the ORIGINAL cloud
+
+
+def test_knn_tiny_clouds(GS):
+    for n in (1, 2, 5, 33):
+        ref = np.random.default_rng(n).random((n, 3)).astype(np.float32)
+        s = GS().setInputCloud(ref)
+        gi, gd, keff = s.nearestKSearch(ref, 4)
+        oi, od, okeff = oracle.brute_knn(ref, ref, 4)
+        assert keff == okeff
+        assert_knn_equal(gi, gd, oi, od)
+    same = np.ones((50, 3), np.float32)                         # zero-extent cloud
+    gi, gd, _ = GS().setInputCloud(same).nearestKSearch(same[:3], 5)
+    assert gi.tolist() == [[0, 1, 2, 3, 4]] * 3 and (gd == 0).all()
+
+
+# ---------------------------------------------------------------- radius
+@pytest.mark.parametrize("radius,hint", [(0.05, 0.05), (0.03, 0.0), (0.12, 0.05)])
+def test_radius_vs_oracle(GS, radius, hint):
+    ref = synth.room(80000, 1001)
+    qry = synth.noisy_copy(ref, 5, 0.003)[:10000]
+    s = GS().setInputCloud(ref, cell_hint=hint)
+    off, idx, d2 = s.radiusSearch(qry, radius)
+    ooff, oidx, od2 = oracle.KdTree(ref).radius(qry, radius)
+    assert np.array_equal(off, ooff) and np.array_equal(idx, oidx) and np.array_equal(bits(d2), bits(od2))
+
+
+def test_radius_boundary_max_nn_empty_unsorted(GS):
+    ref = np.array([[0, 0, 0], [0.5, 0, 0], [1.0, 0, 0], [0, 0.25, 0]], np.float32)
+    qry = np.zeros((1, 3), np.float32)
+    s = GS().setInputCloud(ref)
+    assert s.radiusSearch(qry, 0.5)[1].tolist() == [0, 3]                 # d2 == r2 is excluded
+    assert s.radiusSearch(qry, 0.5000001)[1].tolist() == [0, 3, 1]
+    assert s.radiusSearch(qry, 2.0, max_nn=2)[1].tolist() == [0, 3]
+    off, idx, _ = s.radiusSearch(np.array([[9, 9, 9]], np.float32), 0.1)
+    assert off.tolist() == [0, 0] and idx.size == 0
+    big = synth.room(20000, 9)
+    s2 = GS(sorted=False).setInputCloud(big, cell_hint=0.1)
+    off, idx, d2 = s2.radiusSearch(big[:3000], 0.1)
+    ooff, oidx, od2 = oracle.KdTree(big).radius(big[:3000], 0.1)
+    assert np.array_equal(off, ooff)
+    for i in range(0, 3000, 50):                                            # unsorted rows: same sets
+        assert sorted(idx[off[i]:off[i + 1]].tolist()) == sorted(oidx[off[i]:off[i + 1]].tolist())
+    s3 = GS().setInputCloud(big, cell_hint=0.1)
+    off, idx, d2 = s3.radiusSearch(big[:3000], 0.1, max_nn=5)
+    ooff, oidx, od2 = oracle.KdTree(big).radius(big[:3000], 0.1, max_nn=5)
+    assert np.array_equal(off, ooff) and np.array_equal(idx, oidx) and np.array_equal(bits(d2), bits(od2))
+
+
+# ---------------------------------------------------------------- fused consumers
+@pytest.mark.parametrize("mean_k", [16, 50, 7])
+def test_sor_mean_distance_and_threshold(GS, mean_k):
+    ref = synth.room(100000, 2001)
+    s = GS().setInputCloud(ref, k_hint=mean_k + 1)
+    dist = s.meanNeighbourDistance(None, mean_k)
+    o = oracle.sor(ref, mean_k, 1.5)
+    assert np.array_equal(bits(dist), bits(o["distances"]))                 # fp64 sqrt/sum in the same order: bit-exact
+    r = s.sorThreshold(dist, len(ref), 1.5)
+    for key in ("mean", "stddev", "threshold"):
+        assert abs(r[key] - o[key]) <= 1e-9 * abs(o[key])                   # parallel fp64 reduction order, tolerance 1e-9 rel
+    assert r["kept"] == o["kept"] and np.array_equal(r["keep"].astype(bool), o["keep"])
+
+
+def _normal_err(a, b):
+    return np.linalg.norm(a[:, :3] - b[:, :3], axis=1)
+
+
+def test_normals_knn_vs_oracle(GS):
+    ref = synth.room(60000, 1001)
+    s = GS().setInputCloud(ref, k_hint=50)
+    n = s.normalsKnn(None, 50)
+    o = oracle.normals_knn(ref, 50)
+    # eigen33 uses atan2f/cosf/sinf whose last-ulp rounding differs between glibc and CUDA; tolerance 1e-5 (north_star)
+    # on the unit normal, except where the smallest eigenvalue is (near-)degenerate and the eigenvector is ill-conditioned.
+    err = _normal_err(n, o)
+    assert np.isfinite(n).all()
+    assert np.quantile(err, 0.99) < 1e-5 and (err < 1e-5).mean() > 0.995
+    assert np.allclose(n[:, 3], o[:, 3], rtol=1e-4, atol=1e-6)
+    assert (np.einsum("ij,ij->i", -ref[:, :3], n[:, :3]) >= -1e-6).all()   # flipped towards the viewpoint (origin)
+
+
+def test_normals_radius_and_degenerate(GS):
+    ref = synth.room(40000, 1001)
+    s = GS().setInputCloud(ref, cell_hint=0.03)
+    n = s.normalsRadius(None, 0.03)
+    o = oracle.normals_radius(ref, 0.03)
+    assert np.array_equal(np.isnan(n[:, 0]), np.isnan(o[:, 0]))             # < 3 neighbours -> NaN on both sides
+    ok = ~np.isnan(o[:, 0])
+    err = _normal_err(n[ok], o[ok])
+    assert np.quantile(err, 0.98) < 1e-5
+    lone = np.array([[0, 0, 0], [5, 5, 5]], np.float32)
+    assert np.isnan(GS().setInputCloud(lone).normalsRadius(None, 0.1)).all()
+
+
+def test_euclidean_clusters(GS):
+    rng = np.random.default_rng(1)
+    a = rng.random((300, 3)).astype(np.float32) * 0.1
+    b = a + np.array([0.16, 0, 0], np.float32)
+    pts = np.concatenate([a, b, np.array([[5, 5, 5], [5.01, 5, 5]], np.float32)])
+    for tol, mn, mx in ((0.05, 100, 250000), (0.07, 100, 250000), (0.07, 100, 500), (0.05, 1, 250000)):
+        lab, sizes = GS().setInputCloud(pts, cell_hint=tol).euclideanClusters(tol, mn, mx)
+        olab, osizes = oracle.KdTree(pts).ece(tol, mn, mx)
+        assert np.array_equal(lab, olab) and np.array_equal(sizes, osizes)
+
+
+def test_euclidean_clusters_scene_known_count(GS):
+    pts, ids = synth.scene(400000, 3001, extent=12.0, n_objects=80)
+    s = GS().setInputCloud(pts, cell_hint=0.05)
+    lab, sizes = s.euclideanClusters(0.05, 100, 250000)
+    olab, osizes = oracle.KdTree(pts).ece(0.05, 100, 250000)
+    assert len(sizes) == 80
+    assert np.array_equal(sizes, osizes) and np.array_equal(lab, olab)      # bit-exact labels incl. the PCL ordering
+
+
+def test_icp_step_and_align(GS):
+    src, tgt, T = synth.icp_pair(60000, 4001, size=(5, 5, 3))
+    s = GS().setInputCloud(tgt, k_hint=1)
+    cnt, sums, ci, cd = s.icpStep(src.copy(), None, want_correspondences=True)
+    ocnt, osums, oci, ocd = oracle.KdTree(tgt).icp_pass(src)
+    assert cnt == ocnt and np.array_equal(ci, oci) and np.array_equal(bits(cd), bits(ocd))
+    assert np.allclose(sums, osums, rtol=1e-12, atol=1e-9)                  # fp64 sums, different association only
+    r = s.icpAlign(src, 20)
+    o = oracle.icp(src, tgt, 20)
+    assert r["converged"] == o["converged"] and r["iterations"] == o["iterations"]
+    assert np.allclose(r["T"], o["T"], rtol=1e-5, atol=1e-6)                # tolerance 1e-5 (north_star) on the 4x4
+    assert abs(r["fitness"] - o["fitness"]) <= 1e-5 * o["fitness"]
+    assert np.allclose(r["T"], np.linalg.inv(T), atol=2e-4)
+
+
+def test_first_within(GS):
+    ref = synth.room(30000, 5)
+    q = synth.noisy_copy(ref, 6, 0.02)[:2000]
+    got = GS().setInputCloud(ref, cell_hint=0.05).firstWithin(q, 0.05)
+    assert np.array_equal(got, oracle.first_within(ref, q, 0.05))
+
+
+# ---------------------------------------------------------------- device-pointer path + properties at full size
+def test_device_pointer_path_matches_host_path(GS):
+    import torch
+    ref = synth.room(50000, 11, stride4=True)
+    qry = synth.noisy_copy(ref, 12, 0.002, stride4=True)[:8000]
+    hi, hd, _ = GS().setInputCloud(ref).nearestKSearch(qry, 16)
+    s = GS().setInputCloud(torch.from_numpy(ref).cuda())
+    di, dd, _ = s.nearestKSearch(torch.from_numpy(qry).cuda(), 16)
+    assert np.array_equal(di.cpu().numpy(), hi) and np.array_equal(bits(dd.cpu().numpy()), bits(hd))
+    off, idx, d2 = s.radiusSearch(torch.from_numpy(qry).cuda(), 0.05)
+    ooff, oidx, od2 = oracle.KdTree(ref).radius(qry, 0.05)
+    assert np.array_equal(off.cpu().numpy(), ooff) and np.array_equal(idx.cpu().numpy(), oidx)
+
+
+def test_full_size_properties_10m(GS):
+    """BASELINE headline size (10 M reference points, k = 16): size-independent properties + a sampled oracle check."""
+    import torch
+    ref = synth.room(10_000_000, 4001, size=(10.0, 10.0, 3.0), stride4=True)
+    dref = torch.from_numpy(ref).cuda()
+    s = GS().setInputCloud(dref, k_hint=16)
+    idx, d2, keff = s.nearestKSearch(None, 16)
+    assert keff == 16
+    assert bool((d2[:, 1:] >= d2[:, :-1]).all())                                            # sorted rows
+    assert bool((idx[:, 0] == torch.arange(ref.shape[0], device="cuda", dtype=torch.int32)).all()) or bool((d2[:, 0] == 0).all())
+    assert bool((idx >= 0).all()) and bool((idx < ref.shape[0]).all())
+    srt = torch.sort(idx.long(), dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())                                          # no duplicates in a row
+    # recompute the distances from the returned indices (fp32, same association)
+    sel = torch.randint(0, ref.shape[0], (200000,), device="cuda")
+    p = dref[sel, :3].unsqueeze(1)
+    nb = dref[idx[sel].long(), :3]
+    df = p - nb
+    rec = (df[..., 0] * df[..., 0] + df[..., 1] * df[..., 1]) + df[..., 2] * df[..., 2]
+    assert bool(((rec - d2[sel]).abs() <= 1e-6 * rec.abs() + 1e-12).all())
+    sample = np.random.default_rng(0).choice(ref.shape[0], 20000, replace=False)
+    oi, od, _ = oracle.KdTree(ref).knn(ref[sample], 16)
+    assert np.array_equal(idx[torch.from_numpy(sample).cuda()].cpu().numpy(), oi)
+    assert np.array_equal(bits(d2[torch.from_numpy(sample).cuda()].cpu().numpy()), bits(od))
