@@ -81,6 +81,56 @@ __device__ __forceinline__ void scan_shell(const Grid &g, const QueryCell &c, in
     }
 }
 
+// world d2 -> cell units, rounded up (used as the clipping radius of scan_clipped)
+__device__ __forceinline__ float to_cell_units(const Grid &g, float d2) { return d2 == CUDART_INF_F ? d2 : d2 * g.inv_cell * g.inv_cell * (1.0f + 4e-5f); }
+
+// Next block radius of an exact search whose k-th distance is not yet covered by radius R.  While fewer than k points
+// have been seen the block doubles (a shell row costs ONE run lookup whatever its x-length, so a pass is O(R^2), not
+// O(R^3)); once k points are known the block jumps straight to the radius that covers their ball.
+__device__ __forceinline__ int next_ring(const Grid &g, int R, float kth_d2) {
+    const int cap = max(g.nx, max(g.ny, g.nz));
+    if (kth_d2 == CUDART_INF_F) return min(2 * R + 1, max(cap, R + 1));
+    const float need = sqrtf(to_cell_units(g, kth_d2)) + 0.01f;
+    return max(R + 1, (int)fminf(ceilf(need), (float)cap));
+}
+
+// scan_shell restricted to the ball of squared radius tau_u (CELL units, +inf = no restriction) around the query:
+// a row is skipped when its (y, z) gap alone exceeds the ball and the x-range of a kept row is cut to the cells the
+// ball can reach.  Every test is conservative (2e-3 cell slack + the 4e-5 relative slack of to_cell_units, the same
+// rounding budget as covered_d2), so no point with d2 <= tau is ever skipped.  This is what makes ring >= 2 cheap:
+// a query that misses the 3x3x3 guarantee by a little only touches the one or two cells the ball pokes into.
+template <class F>
+__device__ __forceinline__ void scan_clipped(const Grid &g, const QueryCell &c, int Rin, int Rout, float tau_u, F &&f) {
+    const int z0 = max(c.cz - Rout, 0), z1 = min(c.cz + Rout, g.nz - 1);
+    const int y0 = max(c.cy - Rout, 0), y1 = min(c.cy + Rout, g.ny - 1);
+    const bool clip = tau_u < CUDART_INF_F;
+    for (int z = z0; z <= z1; ++z) {
+        const float gz = fmaxf(fmaxf((float)z - c.uz, c.uz - (float)(z + 1)) - 2e-3f, 0.f);
+        const float gz2 = gz * gz;
+        if (gz2 > tau_u) continue;
+        for (int y = y0; y <= y1; ++y) {
+            const float gy = fmaxf(fmaxf((float)y - c.uy, c.uy - (float)(y + 1)) - 2e-3f, 0.f);
+            const float D = gy * gy + gz2;
+            if (D > tau_u) continue;
+            int xlo = c.cx - Rout, xhi = c.cx + Rout;
+            if (clip) {
+                const float w = sqrtf(tau_u - D) + 2e-3f;
+                xlo = max(xlo, (int)floorf(c.ux - w)); xhi = min(xhi, (int)floorf(c.ux + w));
+            }
+            xlo = max(xlo, 0); xhi = min(xhi, g.nx - 1);
+            const uint32_t *row = g.cell_start + ((size_t)z * g.ny + y) * g.nx;
+            if (max(abs(z - c.cz), abs(y - c.cy)) > Rin) {
+                if (xlo <= xhi) { uint32_t j = __ldg(row + xlo), e = __ldg(row + xhi + 1); for (; j < e; ++j) f(j, __ldg(g.pts + j)); }
+            } else {
+                const int xl = min(xhi, c.cx - Rin - 1);     // left strip [xlo, xl]
+                if (xlo <= xl) { uint32_t j = __ldg(row + xlo), e = __ldg(row + xl + 1); for (; j < e; ++j) f(j, __ldg(g.pts + j)); }
+                const int xr = max(xlo, c.cx + Rin + 1);     // right strip [xr, xhi]
+                if (xr <= xhi) { uint32_t j = __ldg(row + xr), e = __ldg(row + xhi + 1); for (; j < e; ++j) f(j, __ldg(g.pts + j)); }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // top-k containers.  Entries are 64-bit keys (fp32 d2 bits << 32 | payload): d2 >= +0 so the
 // unsigned order of the bits is the numeric order, and one 64-bit compare gives the canonical

@@ -13,6 +13,7 @@
 #include <cstring>
 
 #include "pcc_internal.h"
+#include "pcc_fastknn.cuh"
 
 namespace pcc {
 
@@ -35,35 +36,103 @@ template <class List>
 __device__ __forceinline__ void knn_search(const Grid &g, float x, float y, float z, int k, List &list) {
     const QueryCell c = locate(g, x, y, z);
     int Rin = -1, R = 1;
+    float clip = CUDART_INF_F;      // ball of the current k-th distance (cell units): rings >= 2 only touch cells inside it
     for (;;) {
-        scan_shell(g, c, Rin, R, [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
+        scan_clipped(g, c, Rin, R, clip, [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
         const float cov = covered_d2(g, c, R);
         if (cov == CUDART_INF_F) break;
         const nkey_t kth = list.at(k - 1);
+        clip = to_cell_units(g, key_d2(kth));
         if (kth != PCC_EMPTY_KEY && key_d2(kth) < cov) break;
-        Rin = R; ++R;
+        Rin = R; R = next_ring(g, R, key_d2(kth));
     }
 }
 
 template <int K>
-__global__ void __launch_bounds__(128) knn_reg_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void write_row(const nkey_t (&key)[K], int k, int32_t *__restrict__ oi, float *__restrict__ od, int vec4) {
+    if (vec4 && K >= 4 && k == K) {
+#pragma unroll
+        for (int j = 0; j + 3 < K; j += 4) {
+            reinterpret_cast<int4 *>(oi)[j >> 2] = make_int4(key_idx(key[j]), key_idx(key[j + 1]), key_idx(key[j + 2]), key_idx(key[j + 3]));
+            reinterpret_cast<float4 *>(od)[j >> 2] = make_float4(key_d2(key[j]), key_d2(key[j + 1]), key_d2(key[j + 2]), key_d2(key[j + 3]));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j) if (j < k) { oi[j] = key_idx(key[j]); od[j] = key_d2(key[j]); }
+    }
+}
+// exact path for one query slot t: insertion-sorted 64-bit keys + ring expansion (any density, any tie pattern)
+template <int K>
+__device__ __forceinline__ void knn_reg_body(const Grid &g, const QueryView &v, int64_t t, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4) {
     float x, y, z; int64_t row; bool empty;
     RegList<K> list; list.init();
     const bool live = load_query(g, v, t, x, y, z, row, empty);
     if (!live && !empty) return;
     if (live) knn_search(g, x, y, z, k, list);
-    int32_t *oi = out_idx + row * k; float *od = out_d2 + row * k;
-    if (vec4 && K >= 4 && k == K) {
-#pragma unroll
-        for (int j = 0; j + 3 < K; j += 4) {
-            reinterpret_cast<int4 *>(oi)[j >> 2] = make_int4(key_idx(list.key[j]), key_idx(list.key[j + 1]), key_idx(list.key[j + 2]), key_idx(list.key[j + 3]));
-            reinterpret_cast<float4 *>(od)[j >> 2] = make_float4(key_d2(list.key[j]), key_d2(list.key[j + 1]), key_d2(list.key[j + 2]), key_d2(list.key[j + 3]));
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < K; ++j) if (j < k) { oi[j] = key_idx(list.key[j]); od[j] = key_d2(list.key[j]); }
+    write_row<K>(list.key, k, out_idx + row * k, out_d2 + row * k, vec4);
+}
+template <int K>
+__global__ void __launch_bounds__(128) knn_reg_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4) {
+    knn_reg_body<K>(g, v, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, k, out_idx, out_d2, vec4);
+}
+// queries the fast path could not prove exact (listed by knn_fast_kernel)
+struct FixList { uint32_t *list; unsigned *count; unsigned long long *stats; };   // stats: optional debug counters (PCC_STATS=1)
+template <int K>
+__global__ void __launch_bounds__(128) knn_fixup_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4, FixList fix) {
+    const unsigned n = *fix.count;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) knn_reg_body<K>(g, v, (int64_t)fix.list[i], k, out_idx, out_d2, vec4);
+}
+
+// ---- two-phase path for 2 <= k <= 32 ----
+// phase 1: distances only.  Ring 1 unclipped, every later ring clipped to the ball of the current k-th distance.
+// Returns tau = exact k-th smallest d2 over the whole cloud (+inf if the cloud has fewer than k points) and the
+// block radius R that was needed.
+template <int K>
+__device__ __forceinline__ float kth_distance(const Grid &g, const QueryCell &c, float x, float y, float z, int k, RegDist<K> &list, int &R_out) {
+    int Rin = -1, R = 1;
+    float kth = CUDART_INF_F;
+    for (;;) {
+        scan_clipped(g, c, Rin, R, to_cell_units(g, kth), [&](uint32_t, float4 p) { list.offer(dist2(x, y, z, p.x, p.y, p.z)); });
+        kth = (k == K) ? list.d[K - 1] : list.at(k - 1);
+        const float cov = covered_d2(g, c, R);
+        if (cov == CUDART_INF_F || kth < cov) break;
+        Rin = R; R = next_ring(g, R, kth);
     }
+    R_out = R;
+    return kth;
+}
+static constexpr int kFastThreads = 128;
+template <int K>
+__global__ void __launch_bounds__(kFastThreads) knn_fast_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4, FixList fix) {
+    __shared__ nkey_t sbuf_all[K * kFastThreads];
+    nkey_t *sbuf = sbuf_all + threadIdx.x;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float x, y, z; int64_t row; bool empty;
+    const bool live = load_query(g, v, t, x, y, z, row, empty);
+    if (!live) {
+        if (empty) { nkey_t e[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) e[j] = PCC_EMPTY_KEY;
+            write_row<K>(e, k, out_idx + row * k, out_d2 + row * k, vec4); }
+        return;
+    }
+    const QueryCell c = locate(g, x, y, z);
+    RegDist<K> list; list.init();
+    int R;
+    const float tau = kth_distance<K>(g, c, x, y, z, k, list, R);
+    // phase 2: every point with d2 <= tau lies in the block of radius R and inside the ball: pick up (d2, idx)
+    int cnt = 0;
+    scan_clipped(g, c, -1, R, to_cell_units(g, tau), [&](uint32_t, float4 p) {
+        const float d2 = dist2(x, y, z, p.x, p.y, p.z);
+        if (d2 <= tau) { if (cnt < K) sbuf[cnt * kFastThreads] = make_key(d2, __float_as_uint(p.w)); ++cnt; }
+    });
+    if (fix.stats) { atomicAdd(fix.stats + 0, 1ull); atomicAdd(fix.stats + 4, R > 1 ? 1ull : 0ull); atomicAdd(fix.stats + 5, cnt > K ? 1ull : 0ull); atomicAdd(fix.stats + 6, (unsigned long long)cnt); }
+    if (cnt > K) { fix.list[atomicAdd(fix.count, 1u)] = (uint32_t)t; return; }      // more than K candidates tied at tau: exact path
+    nkey_t e[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) e[j] = j < cnt ? sbuf[j * kFastThreads] : PCC_EMPTY_KEY;
+    bitonic_sort_key<K>(e);
+    write_row<K>(e, k, out_idx + row * k, out_d2 + row * k, vec4);
 }
 
 // 32 < k <= PCC_MAX_K: per-thread max-heap in dynamic shared memory
@@ -77,12 +146,14 @@ __global__ void knn_heap_kernel(Grid g, QueryView v, int k, int32_t *__restrict_
     if (live) {
         const QueryCell c = locate(g, x, y, z);
         int Rin = -1, R = 1;
+        float clip = CUDART_INF_F;
         for (;;) {
-            scan_shell(g, c, Rin, R, [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
+            scan_clipped(g, c, Rin, R, clip, [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
             const float cov = covered_d2(g, c, R);
             if (cov == CUDART_INF_F) break;
             if (list.full() && key_d2(list.worst()) < cov) break;
-            Rin = R; ++R;
+            if (list.full()) clip = to_cell_units(g, key_d2(list.worst()));
+            Rin = R; R = next_ring(g, R, list.full() ? key_d2(list.worst()) : CUDART_INF_F);
         }
     }
     list.finish();
@@ -101,12 +172,15 @@ __global__ void __launch_bounds__(128) mean_dist_reg_kernel(Grid g, QueryView v,
     RegDist<K> list; list.init();
     const QueryCell c = locate(g, x, y, z);
     int Rin = -1, R = 1;
+    float clip = CUDART_INF_F;
     for (;;) {
-        scan_shell(g, c, Rin, R, [&](uint32_t, float4 p) { list.offer(dist2(x, y, z, p.x, p.y, p.z)); });
+        scan_clipped(g, c, Rin, R, clip, [&](uint32_t, float4 p) { list.offer(dist2(x, y, z, p.x, p.y, p.z)); });
         const float cov = covered_d2(g, c, R);
         if (cov == CUDART_INF_F) break;
-        if ((EXACT ? list.d[K - 1] : list.at(mean_k)) < cov) break;
-        Rin = R; ++R;
+        const float kth = EXACT ? list.d[K - 1] : list.at(mean_k);
+        clip = to_cell_units(g, kth);
+        if (kth < cov) break;
+        Rin = R; R = next_ring(g, R, kth);
     }
     double s = 0.0;
     if (EXACT) {
@@ -127,12 +201,14 @@ __global__ void mean_dist_heap_kernel(Grid g, QueryView v, int mean_k, float *__
     HeapList list; list.init(smem_keys + threadIdx.x, blockDim.x, mean_k + 1);
     const QueryCell c = locate(g, x, y, z);
     int Rin = -1, R = 1;
+    float clip = CUDART_INF_F;
     for (;;) {
-        scan_shell(g, c, Rin, R, [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
+        scan_clipped(g, c, Rin, R, clip, [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
         const float cov = covered_d2(g, c, R);
         if (cov == CUDART_INF_F) break;
         if (list.full() && key_d2(list.worst()) < cov) break;
-        Rin = R; ++R;
+        if (list.full()) clip = to_cell_units(g, key_d2(list.worst()));
+        Rin = R; R = next_ring(g, R, list.full() ? key_d2(list.worst()) : CUDART_INF_F);
     }
     list.finish();
     double s = 0.0;
@@ -163,12 +239,14 @@ __global__ void normals_knn_heap_kernel(Grid g, QueryView v, int k, const uint32
     HeapList list; list.init(smem_keys + threadIdx.x, blockDim.x, k);
     const QueryCell c = locate(g, x, y, z);
     int Rin = -1, R = 1;
+    float clip = CUDART_INF_F;
     for (;;) {
-        scan_shell(g, c, Rin, R, [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
+        scan_clipped(g, c, Rin, R, clip, [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
         const float cov = covered_d2(g, c, R);
         if (cov == CUDART_INF_F) break;
         if (list.full() && key_d2(list.worst()) < cov) break;
-        Rin = R; ++R;
+        if (list.full()) clip = to_cell_units(g, key_d2(list.worst()));
+        Rin = R; R = next_ring(g, R, list.full() ? key_d2(list.worst()) : CUDART_INF_F);
     }
     list.finish();
     float a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; int cnt = 0;
@@ -204,14 +282,14 @@ __global__ void __launch_bounds__(kIcpThreads) icp_step_kernel(Grid g, float4 *_
                 const QueryCell c = locate(g, p.x, p.y, p.z);
                 int Rin = -1, R = 1;
                 for (;;) {
-                    scan_shell(g, c, Rin, R, [&](uint32_t pos, float4 r) {
+                    scan_clipped(g, c, Rin, R, to_cell_units(g, key_d2(best)), [&](uint32_t pos, float4 r) {
                         const nkey_t k = make_key(dist2(p.x, p.y, p.z, r.x, r.y, r.z), __float_as_uint(r.w));
                         if (k < best) { best = k; bpos = pos; }
                     });
                     const float cov = covered_d2(g, c, R);
                     if (cov == CUDART_INF_F) break;
                     if (best != PCC_EMPTY_KEY && key_d2(best) < cov) break;
-                    Rin = R; ++R;
+                    Rin = R; R = next_ring(g, R, key_d2(best));
                 }
                 bi = key_idx(best); bd = key_d2(best);
                 if (bi >= 0) {
@@ -288,6 +366,15 @@ static int set_heap_smem(Kern kern) {
 template <int K>
 static void launch_knn_reg(const Grid &g, const QueryView &v, int k, int32_t *oi, float *od, int vec4, cudaStream_t s) {
     knn_reg_kernel<K><<<nblocks(v.nq, 128), 128, 0, s>>>(g, v, k, oi, od, vec4);
+    PCC_LAUNCHED();
+}
+template <int K>
+static void launch_knn_fast(const Grid &g, const QueryView &v, int k, int32_t *oi, float *od, int vec4, FixList fix, cudaStream_t s) {
+    cudaMemsetAsync(fix.count, 0, sizeof(unsigned), s);
+    knn_fast_kernel<K><<<nblocks(v.nq, kFastThreads), kFastThreads, 0, s>>>(g, v, k, oi, od, vec4, fix);
+    PCC_LAUNCHED();
+    knn_fixup_kernel<K><<<148 * 4, 128, 0, s>>>(g, v, k, oi, od, vec4, fix);
+    PCC_LAUNCHED();
 }
 
 }  // namespace pcc
@@ -328,21 +415,41 @@ int pcc_knn(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int k, 
     const int vec4 = ((((uintptr_t)oi) | ((uintptr_t)od)) & 15) == 0 && (k % 4 == 0);
     KernelTimer timer(idx, s);
     if (qs.nq > 0) {
+        static const bool exact_only = getenv("PCC_EXACT_ONLY") != nullptr;     // debugging aid: force the ring-expansion path
+        static const bool want_stats = getenv("PCC_STATS") != nullptr;
+        FixList fix{nullptr, nullptr, nullptr};
+        if (k > 1 && k <= 32 && !exact_only) {
+            PCC_TRY(idx->misc.reserve((size_t)v.nq * 4 + 128));
+            fix.count = idx->misc.as<unsigned>();
+            fix.list = idx->misc.as<uint32_t>() + 32;
+            if (want_stats) { fix.stats = (unsigned long long *)(idx->misc.as<uint32_t>() + 2); PCC_CUDA(cudaMemsetAsync(fix.stats, 0, 64, s)); }
+        }
         if (k == 1) launch_knn_reg<1>(g, v, k, oi, od, vec4, s);
-        else if (k <= 2) launch_knn_reg<2>(g, v, k, oi, od, vec4, s);
-        else if (k <= 4) launch_knn_reg<4>(g, v, k, oi, od, vec4, s);
-        else if (k <= 8) launch_knn_reg<8>(g, v, k, oi, od, vec4, s);
-        else if (k <= 16) launch_knn_reg<16>(g, v, k, oi, od, vec4, s);
-        else if (k <= 32) launch_knn_reg<32>(g, v, k, oi, od, vec4, s);
+        else if (exact_only && k <= 2) launch_knn_reg<2>(g, v, k, oi, od, vec4, s);
+        else if (exact_only && k <= 4) launch_knn_reg<4>(g, v, k, oi, od, vec4, s);
+        else if (exact_only && k <= 8) launch_knn_reg<8>(g, v, k, oi, od, vec4, s);
+        else if (exact_only && k <= 16) launch_knn_reg<16>(g, v, k, oi, od, vec4, s);
+        else if (exact_only && k <= 32) launch_knn_reg<32>(g, v, k, oi, od, vec4, s);
+        else if (k <= 4) launch_knn_fast<4>(g, v, k, oi, od, vec4, fix, s);
+        else if (k <= 8) launch_knn_fast<8>(g, v, k, oi, od, vec4, fix, s);
+        else if (k <= 16) launch_knn_fast<16>(g, v, k, oi, od, vec4, fix, s);
+        else if (k <= 32) launch_knn_fast<32>(g, v, k, oi, od, vec4, fix, s);
         else {
             const int th = heap_threads(k);
             PCC_TRY(set_heap_smem(knn_heap_kernel));
             knn_heap_kernel<<<nblocks(v.nq, th), th, (size_t)k * th * sizeof(nkey_t), s>>>(g, v, k, oi, od);
+            PCC_LAUNCHED();
         }
-        PCC_LAUNCHED();
         PCC_CUDA(cudaGetLastError());
     }
     timer.stop();
+    if (getenv("PCC_STATS") && k > 1 && k <= 32) {
+        unsigned long long h[8];
+        cudaMemcpyAsync(h, idx->misc.as<uint32_t>() + 2, 64, cudaMemcpyDeviceToHost, s); cudaStreamSynchronize(s);
+        const double q = (double)std::max<unsigned long long>(h[0], 1);
+        fprintf(stderr, "[pcc stats] queries=%llu inner_cand/q=%.1f shell_cand/q=%.1f shell_runs/q=%.1f need_ring2=%.3f fixup=%.4f collected/q=%.2f\n",
+                h[0], h[1] / q, h[2] / q, h[3] / q, h[4] / q, h[5] / q, h[6] / q);
+    }
     if (mem == PCC_HOST) {
         PCC_TRY(copy_out(out_idx, oi, cells * 4, mem, s));
         PCC_TRY(copy_out(out_d2, od, cells * 4, mem, s));
