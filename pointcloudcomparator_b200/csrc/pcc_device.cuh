@@ -94,6 +94,15 @@ __device__ __forceinline__ int next_ring(const Grid &g, int R, float kth_d2) {
     return max(R + 1, (int)fminf(ceilf(need), (float)cap));
 }
 
+// one contiguous float4 run, software-pipelined: the load of point j+1 is in flight while point j is processed
+template <class F>
+__device__ __forceinline__ void walk_run(const Grid &g, uint32_t j, uint32_t e, F &&f) {
+    if (j >= e) return;
+    float4 p = __ldg(g.pts + j);
+    for (++j; j < e; ++j) { const float4 q = __ldg(g.pts + j); f(j - 1, p); p = q; }
+    f(e - 1, p);
+}
+
 // scan_shell restricted to the ball of squared radius tau_u (CELL units, +inf = no restriction) around the query:
 // a row is skipped when its (y, z) gap alone exceeds the ball and the x-range of a kept row is cut to the cells the
 // ball can reach.  Every test is conservative (2e-3 cell slack + the 4e-5 relative slack of to_cell_units, the same
@@ -120,12 +129,12 @@ __device__ __forceinline__ void scan_clipped(const Grid &g, const QueryCell &c, 
             xlo = max(xlo, 0); xhi = min(xhi, g.nx - 1);
             const uint32_t *row = g.cell_start + ((size_t)z * g.ny + y) * g.nx;
             if (max(abs(z - c.cz), abs(y - c.cy)) > Rin) {
-                if (xlo <= xhi) { uint32_t j = __ldg(row + xlo), e = __ldg(row + xhi + 1); for (; j < e; ++j) f(j, __ldg(g.pts + j)); }
+                if (xlo <= xhi) walk_run(g, __ldg(row + xlo), __ldg(row + xhi + 1), f);
             } else {
                 const int xl = min(xhi, c.cx - Rin - 1);     // left strip [xlo, xl]
-                if (xlo <= xl) { uint32_t j = __ldg(row + xlo), e = __ldg(row + xl + 1); for (; j < e; ++j) f(j, __ldg(g.pts + j)); }
+                if (xlo <= xl) walk_run(g, __ldg(row + xlo), __ldg(row + xl + 1), f);
                 const int xr = max(xlo, c.cx + Rin + 1);     // right strip [xr, xhi]
-                if (xr <= xhi) { uint32_t j = __ldg(row + xr), e = __ldg(row + xhi + 1); for (; j < e; ++j) f(j, __ldg(g.pts + j)); }
+                if (xr <= xhi) walk_run(g, __ldg(row + xr), __ldg(row + xhi + 1), f);
             }
         }
     }
