@@ -1,0 +1,127 @@
+// C++ host-mirror self-test: exercises pcc::search::GridSearch<PointT> and the consumer drivers exactly the way the
+// reference drives pcl::search::KdTree and its consumers (src/segmentation.cpp:120-131,232-271; src/comparator.cpp:1089-1110,
+// 1523-1541), and checks them against an in-test brute force with the canonical (fp32 d2, index) order.
+// Built by __graft_entry__.build(); run on the GPU box by tests/test_gpu_cpp_host.py.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <utility>
+
+#include "../../include/pcc/grid_search.hpp"
+
+typedef pcc::PointXYZRGB P;
+typedef pcc::PointCloud<P> Cloud;
+
+static unsigned long long rng_state = 88172645463325252ull;
+static float frand() { rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17; return (float)((rng_state >> 11) & 0xFFFFFF) / 16777216.0f; }
+
+static float d2(const P &a, const P &b) { float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z; float r = dx * dx; r = r + dy * dy; r = r + dz * dz; return r; }
+static bool finite(const P &p) { return std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z); }
+static std::vector<std::pair<float, int> > brute(const Cloud &c, const P &q) {
+    std::vector<std::pair<float, int> > v;
+    for (size_t i = 0; i < c.size(); ++i) if (finite(c[i])) v.push_back(std::make_pair(d2(q, c[i]), (int)i));
+    std::sort(v.begin(), v.end());
+    return v;
+}
+#define REQUIRE(cond) do { if (!(cond)) { std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #cond); return 1; } } while (0)
+
+int main() {
+    Cloud::Ptr cloud(new Cloud);
+    for (int i = 0; i < 20000; ++i) {
+        P p; const int s = i % 3;
+        const float u = frand() * 2.f, v = frand() * 1.5f, n = (frand() - 0.5f) * 0.004f;
+        if (s == 0) { p.x = u; p.y = v; p.z = n; } else if (s == 1) { p.x = u; p.y = n; p.z = v; } else { p.x = n; p.y = u; p.z = v; }
+        cloud->push_back(p);
+    }
+    (*cloud)[17].x = std::numeric_limits<float>::quiet_NaN();
+    (*cloud)[4242].z = std::numeric_limits<float>::infinity();
+
+    pcc::search::GridSearch<P>::Ptr tree(new pcc::search::GridSearch<P>());
+    tree->setInputCloud(cloud);
+    REQUIRE(tree->getInputCloud() == cloud);
+    REQUIRE(tree->getName() == "pcc::search::GridSearch");
+
+    // single-point nearestKSearch, all three overload shapes
+    std::vector<int> idx; std::vector<float> dist;
+    for (int t = 0; t < 50; ++t) {
+        P q; q.x = frand() * 2.f; q.y = frand() * 1.5f; q.z = frand() * 0.2f;
+        const int k = 1 + (t % 20);
+        REQUIRE(tree->nearestKSearch(q, k, idx, dist) == k);
+        std::vector<std::pair<float, int> > ref = brute(*cloud, q);
+        for (int j = 0; j < k; ++j) { REQUIRE(idx[j] == ref[j].second); REQUIRE(dist[j] == ref[j].first); }
+    }
+    REQUIRE(tree->nearestKSearch(123, 5, idx, dist) == 5);
+    REQUIRE(idx[0] == 123 && dist[0] == 0.f);
+    REQUIRE(tree->nearestKSearch(*cloud, 77, 3, idx, dist) == 3 && idx[0] == 77);
+    REQUIRE(tree->nearestKSearch((*cloud)[17], 3, idx, dist) == 0);           // NaN query -> no neighbours
+
+    // batched overload (empty indices = whole cloud) against brute force on a sample
+    std::vector<std::vector<int> > bi; std::vector<std::vector<float> > bd;
+    tree->nearestKSearch(*cloud, std::vector<int>(), 8, bi, bd);
+    REQUIRE(bi.size() == cloud->size());
+    for (size_t i = 0; i < cloud->size(); i += 397) {
+        if (!finite((*cloud)[i])) { REQUIRE(bi[i].empty()); continue; }
+        std::vector<std::pair<float, int> > ref = brute(*cloud, (*cloud)[i]);
+        REQUIRE(bi[i].size() == 8);
+        for (int j = 0; j < 8; ++j) { REQUIRE(bi[i][j] == ref[j].second); REQUIRE(bd[i][j] == ref[j].first); }
+    }
+
+    // radiusSearch: strict d2 < float(r*r), sorted by (d2, idx); max_nn keeps the closest
+    const double r = 0.05; const float r2 = (float)(r * r);
+    for (int t = 0; t < 30; ++t) {
+        const P &q = (*cloud)[(size_t)(t * 631 + 5)];
+        const int m = tree->radiusSearch(q, r, idx, dist);
+        std::vector<std::pair<float, int> > ref = brute(*cloud, q);
+        size_t cnt = 0; while (cnt < ref.size() && ref[cnt].first < r2) ++cnt;
+        REQUIRE((size_t)m == cnt);
+        for (size_t j = 0; j < cnt; ++j) { REQUIRE(idx[j] == ref[j].second); REQUIRE(dist[j] == ref[j].first); }
+        REQUIRE(tree->radiusSearch(q, r, idx, dist, 3) == (int)std::min<size_t>(3, cnt));
+        for (size_t j = 0; j < std::min<size_t>(3, cnt); ++j) REQUIRE(idx[j] == ref[j].second);
+    }
+
+    // indices subset: returned indices address the original cloud
+    pcc::search::GridSearch<P>::IndicesPtr sub(new std::vector<int>());
+    for (int i = 0; i < 20000; i += 2) sub->push_back(i);
+    pcc::search::GridSearch<P> tree2;
+    tree2.setInputCloud(cloud, sub);
+    REQUIRE(tree2.nearestKSearch(5, 4, idx, dist) == 4);                       // index 5 of the subset = original point 10
+    REQUIRE(idx[0] == 10);
+    for (int j = 0; j < 4; ++j) REQUIRE(idx[j] % 2 == 0);
+
+    // consumers
+    pcc::NormalEstimation<P> ne; ne.setSearchMethod(tree); ne.setInputCloud(cloud); ne.setKSearch(50);
+    std::vector<pcc::Normal> normals; ne.compute(normals);
+    REQUIRE(normals.size() == cloud->size());
+    size_t nan_normals = 0;
+    for (size_t i = 0; i < normals.size(); ++i) {
+        if (std::isnan(normals[i].normal_x)) { ++nan_normals; continue; }
+        const float len = normals[i].normal_x * normals[i].normal_x + normals[i].normal_y * normals[i].normal_y + normals[i].normal_z * normals[i].normal_z;
+        REQUIRE(std::fabs(len - 1.f) < 1e-3f);
+    }
+    REQUIRE(nan_normals == 2);                                                  // exactly the two non-finite points
+
+    pcc::StatisticalOutlierRemoval<P> sor; sor.setInputCloud(cloud); sor.setMeanK(50); sor.setStddevMulThresh(1.5);
+    std::vector<int> kept; sor.filter(kept);
+    REQUIRE(!kept.empty() && kept.size() < cloud->size() && sor.mean() > 0 && sor.stddev() > 0);
+
+    Cloud::Ptr blobs(new Cloud);
+    for (int i = 0; i < 600; ++i) { P p; p.x = frand() * 0.1f + (i < 300 ? 0.f : 0.16f); p.y = frand() * 0.1f; p.z = frand() * 0.1f; blobs->push_back(p); }
+    pcc::EuclideanClusterExtraction<P> ec; ec.setClusterTolerance(0.05); ec.setMinClusterSize(100); ec.setMaxClusterSize(250000); ec.setInputCloud(blobs);
+    std::vector<pcc::PointIndices> clusters; ec.extract(clusters);
+    REQUIRE(clusters.size() == 2 && clusters[0].indices.size() == 300 && clusters[1].indices.size() == 300);
+    REQUIRE(std::is_sorted(clusters[0].indices.begin(), clusters[0].indices.end()));
+
+    Cloud::Ptr moved(new Cloud);
+    for (size_t i = 0; i < cloud->size(); i += 4) { P p = (*cloud)[i]; if (!finite(p)) continue; p.x += 0.01f; p.y -= 0.005f; moved->push_back(p); }
+    pcc::IterativeClosestPoint<P> icp; icp.setMaximumIterations(20); icp.setInputSource(moved); icp.setInputTarget(cloud); icp.align();
+    REQUIRE(icp.hasConverged());
+    const float *T = icp.getFinalTransformation();
+    REQUIRE(std::fabs(T[3] + 0.01f) < 2e-3f && std::fabs(T[7] - 0.005f) < 2e-3f && icp.getFitnessScore() < 1e-5);
+
+    std::vector<int> tab; std::vector<float> tabd;
+    REQUIRE(pcc::findPointNeighbours(*tree, 100, tab, tabd) == 100 && tab.size() == cloud->size() * 100);
+
+    std::printf("PASS grid_search host mirror: kNN/radius/indices/normals/SOR/ECE/ICP/neighbour-table (%lld kernel launches)\n", (long long)pcc_launch_count());
+    return 0;
+}
