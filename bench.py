@@ -147,7 +147,12 @@ def run_reference(args):
                              "sample": f"each step = {sample} of the {args.nq} queries against the full {args.n}-point kd-tree; restated FLANN KDTreeSingleIndex "
                                        f"(PCL 1.7 / FLANN cannot be built in this image), {cores} OpenMP threads"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def _dbg(msg):
+    if os.environ.get("PCC_BENCH_DEBUG"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
 
 
 def run_ours(args):
@@ -165,7 +170,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 
+    _dbg("process group up")
     ref, qry = make_clouds(args, rank)
+    _dbg("clouds generated")
     dqry = torch.from_numpy(qry).cuda()
     s = GridSearch(local)
     torch.cuda.synchronize()
@@ -175,9 +182,11 @@ def run_ours(args):
         s.setInputCloud(dref, k_hint=args.k)
     torch.cuda.synchronize()
     build_ms = 1e3 * (time.perf_counter() - t0)
+    _dbg("index built")
     if world > 1:
         shard.broadcast_grid(s, src=0)
     grid = s.grid_info()
+    _dbg(f"grid ready {grid}")
 
     def barrier():
         if world > 1:
@@ -185,12 +194,12 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident steps -------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                      # samples cover warm-up + timed steps + the kernel-timing re-run
     for _ in range(args.warmup):
         out = s.nearestKSearch(dqry, args.k)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -200,13 +209,13 @@ def run_ours(args):
     barrier()
     launches = launch_count() - l0
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms = float(tmax.item())
     value = world * args.nq * args.steps / (ms * 1e-3)
 
+    _dbg(f"timed steps done {ms:.2f} ms")
     # ---- the dominant kernel alone (library-side CUDA events on the launch stream) -------------
     s.setTiming(True)
     kms = []
@@ -214,6 +223,7 @@ def run_ours(args):
         s.nearestKSearch(dqry, args.k)
         kms.append(s.lastKernelMs())
     s.setTiming(False)
+    clocks = sampler.stop() if rank == 0 else None
     kernel_ms = float(np.mean(kms))
     peak, peak_src = measured_peak()
     bytes_per_query = 16.0 * args.n / args.nq + 16 + 8 * args.k
@@ -253,6 +263,7 @@ def run_ours(args):
     e2e_value = world * args.nq * e2e_steps / float(te.item())
     checksum = int(hidx[:: max(args.nq // 1000, 1), 0].long().sum())
 
+    _dbg("e2e done")
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -263,26 +274,43 @@ def run_ours(args):
                     "steps": e2e_steps, "how": "pcc_knn(PCC_HOST) with pinned host query / result buffers; H2D + sort + kernel + D2H inside the timed region", "checksum": checksum},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": f"pcc::knn_reg_kernel<{args.k}>", "kernel_ms": kernel_ms, "bytes_per_query": bytes_per_query, "peak_source": peak_src,
+                         "kernel": f"pcc::knn_fast_kernel<{args.k}> (+ knn_fixup_kernel for tie overflow)", "kernel_ms": kernel_ms, "bytes_per_query": bytes_per_query, "peak_source": peak_src,
                          "how": "algorithmic bytes Q*(16*N/Q + 16 + 8k) / mean kernel time over the same steps re-run with library-side CUDA events around the launch"},
             "build_ms": build_ms, "grid": grid,
         }
         if world == 1 and not args.no_cpu:
             cb, _, _ = cpu_baseline(ref, qry, args.k)
             line["cpu_baseline"] = cb
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Route everything libraries print on fd 1 (e.g. NCCL's version banner) to stderr; the JSON line alone goes to stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=10_000_000, help="reference points")
-    ap.add_argument("--nq", type=int, default=10_000_000, help="queries per GPU")
+    ap.add_argument("--ref-points", dest="n", type=int, default=10_000_000, help="reference points")
+    ap.add_argument("--queries", dest="nq", type=int, default=10_000_000, help="queries per GPU")
     ap.add_argument("--k", type=int, default=K)
     ap.add_argument("--cloud", default="surface", choices=["surface", "uniform"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
