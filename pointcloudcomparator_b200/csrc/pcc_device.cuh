@@ -94,13 +94,21 @@ __device__ __forceinline__ int next_ring(const Grid &g, int R, float kth_d2) {
     return max(R + 1, (int)fminf(ceilf(need), (float)cap));
 }
 
-// one contiguous float4 run, software-pipelined: the load of point j+1 is in flight while point j is processed
+// one contiguous float4 run: points are fetched four at a time (independent 16-byte loads in flight together) and
+// then processed in order, which hides most of the L1/L2 latency a one-at-a-time walk exposes
 template <class F>
 __device__ __forceinline__ void walk_run(const Grid &g, uint32_t j, uint32_t e, F &&f) {
-    if (j >= e) return;
-    float4 p = __ldg(g.pts + j);
-    for (++j; j < e; ++j) { const float4 q = __ldg(g.pts + j); f(j - 1, p); p = q; }
-    f(e - 1, p);
+    for (; j + 4 <= e; j += 4) {
+        const float4 p0 = __ldg(g.pts + j), p1 = __ldg(g.pts + j + 1), p2 = __ldg(g.pts + j + 2), p3 = __ldg(g.pts + j + 3);
+        f(j, p0); f(j + 1, p1); f(j + 2, p2); f(j + 3, p3);
+    }
+    if (j < e) {
+        const float4 p0 = __ldg(g.pts + j);
+        const float4 p1 = __ldg(g.pts + min(j + 1, e - 1)), p2 = __ldg(g.pts + min(j + 2, e - 1));
+        f(j, p0);
+        if (j + 1 < e) f(j + 1, p1);
+        if (j + 2 < e) f(j + 2, p2);
+    }
 }
 
 // scan_shell restricted to the ball of squared radius tau_u (CELL units, +inf = no restriction) around the query:
@@ -108,35 +116,51 @@ __device__ __forceinline__ void walk_run(const Grid &g, uint32_t j, uint32_t e, 
 // ball can reach.  Every test is conservative (2e-3 cell slack + the 4e-5 relative slack of to_cell_units, the same
 // rounding budget as covered_d2), so no point with d2 <= tau is ever skipped.  This is what makes ring >= 2 cheap:
 // a query that misses the 3x3x3 guarantee by a little only touches the one or two cells the ball pokes into.
+// Rows are visited centre-out (offsets 0, -1, +1, -2, +2, ...): the nearest rows come first, so the running k-th distance
+// tightens early and fewer later candidates pass the insertion guard.
+__device__ __forceinline__ int centre_out(int a) { return (a & 1) ? -((a + 1) >> 1) : (a >> 1); }
+struct RowRuns { uint32_t j1, e1, j2, e2; };
+// run bounds of row (az, ay) of the block (centre-out numbering); empty runs (j == e) for skipped rows
+__device__ __forceinline__ RowRuns row_runs(const Grid &g, const QueryCell &c, int Rin, int Rout, float tau_u, int az, int ay) {
+    RowRuns r; r.j1 = r.e1 = r.j2 = r.e2 = 0;
+    const int dz = centre_out(az), z = c.cz + dz, dy = centre_out(ay), y = c.cy + dy;
+    if (z < 0 || z >= g.nz || y < 0 || y >= g.ny) return r;
+    const float gz = fmaxf(fmaxf((float)z - c.uz, c.uz - (float)(z + 1)) - 2e-3f, 0.f);
+    const float gy = fmaxf(fmaxf((float)y - c.uy, c.uy - (float)(y + 1)) - 2e-3f, 0.f);
+    const float D = gy * gy + gz * gz;
+    if (D > tau_u) return r;
+    int xlo = c.cx - Rout, xhi = c.cx + Rout;
+    if (tau_u < CUDART_INF_F) {
+        const float w = sqrtf(tau_u - D) + 2e-3f;
+        xlo = max(xlo, (int)floorf(c.ux - w)); xhi = min(xhi, (int)floorf(c.ux + w));
+    }
+    xlo = max(xlo, 0); xhi = min(xhi, g.nx - 1);
+    const uint32_t *row = g.cell_start + ((size_t)z * g.ny + y) * g.nx;
+    if (max(abs(dz), abs(dy)) > Rin) {
+        if (xlo <= xhi) { r.j1 = __ldg(row + xlo); r.e1 = __ldg(row + xhi + 1); }
+    } else {
+        const int xl = min(xhi, c.cx - Rin - 1);     // left strip [xlo, xl]
+        if (xlo <= xl) { r.j1 = __ldg(row + xlo); r.e1 = __ldg(row + xl + 1); }
+        const int xr = max(xlo, c.cx + Rin + 1);     // right strip [xr, xhi]
+        if (xr <= xhi) { r.j2 = __ldg(row + xr); r.e2 = __ldg(row + xhi + 1); }
+    }
+    return r;
+}
+// The row loop is software-pipelined: the cell_start loads of row i+1 are issued before row i is walked, so the
+// dependent load chain (table -> points) of the next row overlaps the arithmetic of the current one.
 template <class F>
 __device__ __forceinline__ void scan_clipped(const Grid &g, const QueryCell &c, int Rin, int Rout, float tau_u, F &&f) {
-    const int z0 = max(c.cz - Rout, 0), z1 = min(c.cz + Rout, g.nz - 1);
-    const int y0 = max(c.cy - Rout, 0), y1 = min(c.cy + Rout, g.ny - 1);
-    const bool clip = tau_u < CUDART_INF_F;
-    for (int z = z0; z <= z1; ++z) {
-        const float gz = fmaxf(fmaxf((float)z - c.uz, c.uz - (float)(z + 1)) - 2e-3f, 0.f);
-        const float gz2 = gz * gz;
-        if (gz2 > tau_u) continue;
-        for (int y = y0; y <= y1; ++y) {
-            const float gy = fmaxf(fmaxf((float)y - c.uy, c.uy - (float)(y + 1)) - 2e-3f, 0.f);
-            const float D = gy * gy + gz2;
-            if (D > tau_u) continue;
-            int xlo = c.cx - Rout, xhi = c.cx + Rout;
-            if (clip) {
-                const float w = sqrtf(tau_u - D) + 2e-3f;
-                xlo = max(xlo, (int)floorf(c.ux - w)); xhi = min(xhi, (int)floorf(c.ux + w));
-            }
-            xlo = max(xlo, 0); xhi = min(xhi, g.nx - 1);
-            const uint32_t *row = g.cell_start + ((size_t)z * g.ny + y) * g.nx;
-            if (max(abs(z - c.cz), abs(y - c.cy)) > Rin) {
-                if (xlo <= xhi) walk_run(g, __ldg(row + xlo), __ldg(row + xhi + 1), f);
-            } else {
-                const int xl = min(xhi, c.cx - Rin - 1);     // left strip [xlo, xl]
-                if (xlo <= xl) walk_run(g, __ldg(row + xlo), __ldg(row + xl + 1), f);
-                const int xr = max(xlo, c.cx + Rin + 1);     // right strip [xr, xhi]
-                if (xr <= xhi) walk_run(g, __ldg(row + xr), __ldg(row + xhi + 1), f);
-            }
-        }
+    const int n1 = 2 * Rout + 1;
+    int az = 0, ay = 0;
+    RowRuns nxt = row_runs(g, c, Rin, Rout, tau_u, 0, 0);
+    for (;;) {
+        const RowRuns cur = nxt;
+        if (++ay == n1) { ay = 0; ++az; }
+        const bool more = az < n1;
+        if (more) nxt = row_runs(g, c, Rin, Rout, tau_u, az, ay);
+        walk_run(g, cur.j1, cur.e1, f);
+        walk_run(g, cur.j2, cur.e2, f);
+        if (!more) break;
     }
 }
 
@@ -217,13 +241,12 @@ struct RegDist {
 #pragma unroll
         for (int i = 0; i < K; ++i) d[i] = CUDART_INF_F;
     }
-    __device__ __forceinline__ void offer(float c) {
-        if (c < d[K - 1]) {
+    __device__ __forceinline__ void insert(float c) {          // unguarded: a no-op when c >= d[K-1]
 #pragma unroll
-            for (int i = K - 1; i > 0; --i) d[i] = fminf(d[i], fmaxf(d[i - 1], c));
-            d[0] = fminf(d[0], c);
-        }
+        for (int i = K - 1; i > 0; --i) d[i] = fminf(d[i], fmaxf(d[i - 1], c));
+        d[0] = fminf(d[0], c);
     }
+    __device__ __forceinline__ void offer(float c) { if (c < d[K - 1]) insert(c); }
     __device__ __forceinline__ float at(int j) const {
         float r = d[0];
 #pragma unroll

@@ -85,14 +85,33 @@ __global__ void __launch_bounds__(128) knn_fixup_kernel(Grid g, QueryView v, int
 
 // ---- two-phase path for 2 <= k <= 32 ----
 // phase 1: distances only.  Ring 1 unclipped, every later ring clipped to the ball of the current k-th distance.
-// Returns tau = exact k-th smallest d2 over the whole cloud (+inf if the cloud has fewer than k points) and the
-// block radius R that was needed.
+// Every candidate that is not beyond the current k-th distance is also LOGGED (its position in the sorted array, 4 bytes,
+// slot-major shared memory): the final neighbours are a subset of the logged candidates (the k-th distance only shrinks),
+// and a query logs ~k(1 + ln(M/k)) of its M candidates, so phase 2 re-visits ~45 points instead of re-walking ~105.
+// Returns tau = exact k-th smallest d2 over the whole cloud (+inf if the cloud has fewer than k points), the block radius
+// R that proved it, and the number of logged candidates (> L means the log overflowed and is incomplete).
+// launch shape per list size: 32 KB of log per block either way (64 slots x 128 threads, or 128 slots x 64 threads)
+#ifndef PCC_LOG16
+#define PCC_LOG16 48
+#endif
+#ifndef PCC_MB16
+#define PCC_MB16 9
+#endif
+template <int K> struct FastCfg { static constexpr int threads = K <= 16 ? 128 : 64, log_slots = K <= 16 ? PCC_LOG16 : 128, min_blocks = K <= 16 ? PCC_MB16 : 7; };
 template <int K>
-__device__ __forceinline__ float kth_distance(const Grid &g, const QueryCell &c, float x, float y, float z, int k, RegDist<K> &list, int &R_out) {
+__device__ __forceinline__ float kth_distance(const Grid &g, const QueryCell &c, float x, float y, float z, int k, RegDist<K> &list, int &R_out,
+                                              uint32_t *__restrict__ slog, int &nlog) {
     int Rin = -1, R = 1;
     float kth = CUDART_INF_F;
     for (;;) {
-        scan_clipped(g, c, Rin, R, to_cell_units(g, kth), [&](uint32_t, float4 p) { list.offer(dist2(x, y, z, p.x, p.y, p.z)); });
+        scan_clipped(g, c, Rin, R, to_cell_units(g, kth), [&](uint32_t pos, float4 p) {
+            const float d2 = dist2(x, y, z, p.x, p.y, p.z);
+            if (d2 <= list.d[K - 1]) {            // "<=": a candidate tied with the final k-th distance must be in the log too
+                if (nlog < FastCfg<K>::log_slots) slog[nlog * FastCfg<K>::threads] = pos;
+                ++nlog;
+                list.insert(d2);
+            }
+        });
         kth = (k == K) ? list.d[K - 1] : list.at(k - 1);
         const float cov = covered_d2(g, c, R);
         if (cov == CUDART_INF_F || kth < cov) break;
@@ -101,11 +120,13 @@ __device__ __forceinline__ float kth_distance(const Grid &g, const QueryCell &c,
     R_out = R;
     return kth;
 }
-static constexpr int kFastThreads = 128;
+// measured on B200 (10 M queries, k = 16): 96 registers / 5 blocks per SM 6.44 ms, 79 / 6 blocks 5.85 ms, 64 / 8 blocks 5.51 ms --
+// the kernel is latency- and issue-bound, so occupancy is worth a few spilled words
 template <int K>
-__global__ void __launch_bounds__(kFastThreads) knn_fast_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4, FixList fix) {
-    __shared__ nkey_t sbuf_all[K * kFastThreads];
-    nkey_t *sbuf = sbuf_all + threadIdx.x;
+__global__ void __launch_bounds__(FastCfg<K>::threads, FastCfg<K>::min_blocks) knn_fast_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4, FixList fix) {
+    constexpr int kFastThreads = FastCfg<K>::threads, kLogSlots = FastCfg<K>::log_slots;
+    __shared__ uint32_t slog_all[kLogSlots * kFastThreads];
+    uint32_t *slog = slog_all + threadIdx.x;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float x, y, z; int64_t row; bool empty;
     const bool live = load_query(g, v, t, x, y, z, row, empty);
@@ -118,19 +139,30 @@ __global__ void __launch_bounds__(kFastThreads) knn_fast_kernel(Grid g, QueryVie
     }
     const QueryCell c = locate(g, x, y, z);
     RegDist<K> list; list.init();
-    int R;
-    const float tau = kth_distance<K>(g, c, x, y, z, k, list, R);
-    // phase 2: every point with d2 <= tau lies in the block of radius R and inside the ball: pick up (d2, idx)
-    int cnt = 0;
-    scan_clipped(g, c, -1, R, to_cell_units(g, tau), [&](uint32_t, float4 p) {
-        const float d2 = dist2(x, y, z, p.x, p.y, p.z);
-        if (d2 <= tau) { if (cnt < K) sbuf[cnt * kFastThreads] = make_key(d2, __float_as_uint(p.w)); ++cnt; }
-    });
-    if (fix.stats) { atomicAdd(fix.stats + 0, 1ull); atomicAdd(fix.stats + 4, R > 1 ? 1ull : 0ull); atomicAdd(fix.stats + 5, cnt > K ? 1ull : 0ull); atomicAdd(fix.stats + 6, (unsigned long long)cnt); }
-    if (cnt > K) { fix.list[atomicAdd(fix.count, 1u)] = (uint32_t)t; return; }      // more than K candidates tied at tau: exact path
+    int R, nlog = 0;
+    const float tau = kth_distance<K>(g, c, x, y, z, k, list, R, slog, nlog);
+    // phase 2: keep the logged candidates with d2 <= tau (compacted in place: the m-th survivor never overtakes the read index)
+    int m = 0;
+    if (nlog <= kLogSlots) {
+        for (int i = 0; i < nlog; ++i) {
+            const uint32_t pos = slog[i * kFastThreads];
+            const float4 p = __ldg(g.pts + pos);
+            if (dist2(x, y, z, p.x, p.y, p.z) <= tau) { slog[m * kFastThreads] = pos; ++m; }
+        }
+    } else {
+        // log overflow (adversarial visiting order or heavy ties): re-walk the block of radius R inside the tau-ball instead
+        scan_clipped(g, c, -1, R, to_cell_units(g, tau), [&](uint32_t pos, float4 p) {
+            if (dist2(x, y, z, p.x, p.y, p.z) <= tau) { if (m < kLogSlots) slog[m * kFastThreads] = pos; ++m; }
+        });
+    }
+    if (fix.stats) { atomicAdd(fix.stats + 0, 1ull); atomicAdd(fix.stats + 1, (unsigned long long)nlog); atomicAdd(fix.stats + 4, R > 1 ? 1ull : 0ull); atomicAdd(fix.stats + 5, m > K ? 1ull : 0ull); atomicAdd(fix.stats + 6, (unsigned long long)m); atomicAdd(fix.stats + 3, nlog > kLogSlots ? 1ull : 0ull); }
+    if (m > K) { fix.list[atomicAdd(fix.count, 1u)] = (uint32_t)t; return; }      // more than K candidates tied at tau: exact path
     nkey_t e[K];
 #pragma unroll
-    for (int j = 0; j < K; ++j) e[j] = j < cnt ? sbuf[j * kFastThreads] : PCC_EMPTY_KEY;
+    for (int j = 0; j < K; ++j) {
+        e[j] = PCC_EMPTY_KEY;
+        if (j < m) { const float4 p = __ldg(g.pts + slog[j * kFastThreads]); e[j] = make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w)); }
+    }
     bitonic_sort_key<K>(e);
     write_row<K>(e, k, out_idx + row * k, out_d2 + row * k, vec4);
 }
@@ -164,7 +196,7 @@ __global__ void knn_heap_kernel(Grid g, QueryView v, int k, int32_t *__restrict_
 // ---- fused: StatisticalOutlierRemoval first pass (mean distance to the mean_k nearest, self dropped) ----
 // EXACT: mean_k == K - 1 (the instantiated sizes match mean_k = 1, 4, 8, 16, 32, 50), every list index is static.
 template <int K, bool EXACT>
-__global__ void __launch_bounds__(128) mean_dist_reg_kernel(Grid g, QueryView v, int mean_k, float *__restrict__ out) {
+__global__ void __launch_bounds__(128, (K <= 17 ? 8 : (K <= 33 ? 6 : 4))) mean_dist_reg_kernel(Grid g, QueryView v, int mean_k, float *__restrict__ out) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float x, y, z; int64_t row; bool empty;
     const bool live = load_query(g, v, t, x, y, z, row, empty);
@@ -371,7 +403,7 @@ static void launch_knn_reg(const Grid &g, const QueryView &v, int k, int32_t *oi
 template <int K>
 static void launch_knn_fast(const Grid &g, const QueryView &v, int k, int32_t *oi, float *od, int vec4, FixList fix, cudaStream_t s) {
     cudaMemsetAsync(fix.count, 0, sizeof(unsigned), s);
-    knn_fast_kernel<K><<<nblocks(v.nq, kFastThreads), kFastThreads, 0, s>>>(g, v, k, oi, od, vec4, fix);
+    knn_fast_kernel<K><<<nblocks(v.nq, FastCfg<K>::threads), FastCfg<K>::threads, 0, s>>>(g, v, k, oi, od, vec4, fix);
     PCC_LAUNCHED();
     knn_fixup_kernel<K><<<148 * 4, 128, 0, s>>>(g, v, k, oi, od, vec4, fix);
     PCC_LAUNCHED();
@@ -447,8 +479,8 @@ int pcc_knn(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int k, 
         unsigned long long h[8];
         cudaMemcpyAsync(h, idx->misc.as<uint32_t>() + 2, 64, cudaMemcpyDeviceToHost, s); cudaStreamSynchronize(s);
         const double q = (double)std::max<unsigned long long>(h[0], 1);
-        fprintf(stderr, "[pcc stats] queries=%llu inner_cand/q=%.1f shell_cand/q=%.1f shell_runs/q=%.1f need_ring2=%.3f fixup=%.4f collected/q=%.2f\n",
-                h[0], h[1] / q, h[2] / q, h[3] / q, h[4] / q, h[5] / q, h[6] / q);
+        fprintf(stderr, "[pcc stats] queries=%llu logged/q=%.1f log_overflow=%.5f need_ring2=%.3f fixup=%.5f members/q=%.2f\n",
+                h[0], h[1] / q, h[3] / q, h[4] / q, h[5] / q, h[6] / q);
     }
     if (mem == PCC_HOST) {
         PCC_TRY(copy_out(out_idx, oi, cells * 4, mem, s));
