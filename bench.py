@@ -55,7 +55,7 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks + throttle reasons sampled every 50 ms from before the warm-up until after the kernel-timing re-run."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu: int):
@@ -63,7 +63,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
         except Exception:
@@ -197,6 +197,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                      # samples cover warm-up + timed steps + the kernel-timing re-run
+        time.sleep(0.4)                      # let nvidia-smi attach before the first launch
     for _ in range(args.warmup):
         out = s.nearestKSearch(dqry, args.k)
     barrier()

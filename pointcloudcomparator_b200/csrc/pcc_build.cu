@@ -15,7 +15,7 @@
 namespace pcc {
 
 thread_local std::string g_error;
-int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};
 
 int fail(int code, const char *fmt, ...) {
     char buf[1024];
@@ -191,7 +191,7 @@ extern "C" {
 
 const char *pcc_last_error(void) { return g_error.c_str(); }
 int pcc_version(void) { return 100; }
-int64_t pcc_launch_count(void) { return g_launches; }
+int64_t pcc_launch_count(void) { return g_launches.load(); }
 
 int pcc_create(int device, pcc_index **out) {
     if (!out) return fail(PCC_ERR_INVALID, "out is NULL");

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/pcc/search.h"
@@ -11,7 +12,7 @@
 namespace pcc {
 
 extern thread_local std::string g_error;
-extern int64_t g_launches;
+extern std::atomic<int64_t> g_launches;
 int fail(int code, const char *fmt, ...);
 
 #define PCC_CUDA(expr)                                                                                   \

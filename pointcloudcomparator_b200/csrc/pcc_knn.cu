@@ -390,8 +390,7 @@ static int heap_threads(int k) {
 }
 template <class Kern>
 static int set_heap_smem(Kern kern) {
-    static bool done = false;   // per kernel instantiation
-    if (!done) { PCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); done = true; }
+    PCC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));   // per device: set on every launch (cheap)
     return PCC_OK;
 }
 

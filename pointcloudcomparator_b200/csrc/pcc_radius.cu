@@ -198,8 +198,7 @@ static int radius_rows(pcc_index *idx, const Queries &qs, double radius, unsigne
     if (capped) {
         if (max_nn > PCC_MAX_K) return fail(PCC_ERR_INVALID, "max_nn=%u above %d is only supported when it is >= the indexed point count", max_nn, PCC_MAX_K);
         const int th = heap_threads((int)max_nn);
-        static bool attr = false;
-        if (!attr) { PCC_CUDA(cudaFuncSetAttribute(radius_capped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+        PCC_CUDA(cudaFuncSetAttribute(radius_capped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         radius_capped_kernel<<<nblocks(qs.nq, th), th, (size_t)max_nn * th * sizeof(nkey_t), s>>>(idx->grid(), view_of(qs), r2, ring0(idx, radius), (int)max_nn, d_offsets, keys);
         PCC_LAUNCHED();
         PCC_CUDA(cudaGetLastError());
