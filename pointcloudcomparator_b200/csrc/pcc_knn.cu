@@ -97,7 +97,13 @@ __global__ void __launch_bounds__(128) knn_fixup_kernel(Grid g, QueryView v, int
 #ifndef PCC_MB16
 #define PCC_MB16 9
 #endif
-template <int K> struct FastCfg { static constexpr int threads = K <= 16 ? 128 : 64, log_slots = K <= 16 ? PCC_LOG16 : 128, min_blocks = K <= 16 ? PCC_MB16 : 7; };
+#ifndef PCC_LOG32
+#define PCC_LOG32 80
+#endif
+#ifndef PCC_MB32
+#define PCC_MB32 5
+#endif
+template <int K> struct FastCfg { static constexpr int threads = 128, log_slots = K <= 16 ? PCC_LOG16 : PCC_LOG32, min_blocks = K <= 16 ? PCC_MB16 : PCC_MB32; };
 template <int K>
 __device__ __forceinline__ float kth_distance(const Grid &g, const QueryCell &c, float x, float y, float z, int k, RegDist<K> &list, int &R_out,
                                               uint32_t *__restrict__ slog, int &nlog) {
