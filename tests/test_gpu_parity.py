@@ -294,3 +294,53 @@ def test_full_size_properties_10m(GS):
     oi, od, _ = oracle.KdTree(ref).knn(ref[sample], 16)
     assert np.array_equal(idx[torch.from_numpy(sample).cuda()].cpu().numpy(), oi)
     assert np.array_equal(bits(d2[torch.from_numpy(sample).cuda()].cpu().numpy()), bits(od))
+
+
+# ---------------------------------------------------------------- randomized stress (fp32 margins, odd shapes)
+def _stress_cloud(rng, kind, n):
+    if kind == "big_offset":                      # coordinates ~1e4 with centimetre structure: fp32 grid-coordinate rounding
+        return (rng.random((n, 3)) * [3.0, 2.0, 1.0] + [12345.0, -9876.0, 4321.0]).astype(np.float32)
+    if kind == "flat":                            # degenerate z extent
+        p = rng.random((n, 3)) * [5.0, 5.0, 0.0]
+        return p.astype(np.float32)
+    if kind == "line":                            # 1-D manifold
+        t = rng.random(n)
+        return np.stack([t * 7.0, 0.3 * np.sin(t * 20), 0.1 * t], 1).astype(np.float32)
+    if kind == "anisotropic":                     # 1e3 : 1 : 1e-3 extents
+        return (rng.random((n, 3)) * [1000.0, 1.0, 1e-3]).astype(np.float32)
+    if kind == "clustered":                       # very uneven density + far outliers
+        c = rng.normal(0, 1.0, (8, 3))
+        p = c[rng.integers(0, 8, n)] + rng.normal(0, 0.01, (n, 3)) * rng.choice([1.0, 10.0], (n, 1))
+        p[: n // 100] = rng.uniform(-30, 30, (n // 100, 3))
+        return p.astype(np.float32)
+    if kind == "quantized":                       # millimetre-quantized scanner output: many exact ties and duplicates
+        return (np.round(rng.random((n, 3)) * [2.0, 2.0, 0.5] * 200) / 200).astype(np.float32)
+    if kind == "tiny_scale":                      # micrometre-scale cloud
+        return (rng.random((n, 3)) * 1e-4).astype(np.float32)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["big_offset", "flat", "line", "anisotropic", "clustered", "quantized", "tiny_scale"])
+def test_randomized_stress_knn_and_radius(GS, kind):
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(kind.encode()))          # stable per-kind seed
+    ref = _stress_cloud(rng, kind, 30000)
+    spread = np.maximum(ref.max(0) - ref.min(0), 1e-9)
+    qry = np.concatenate([ref[rng.integers(0, len(ref), 1500)] + rng.normal(0, 1e-3, (1500, 3)) * spread,
+                          ref[:500],
+                          ref.min(0) + rng.uniform(-0.5, 1.5, (500, 3)) * spread]).astype(np.float32)
+    tree = oracle.KdTree(ref)
+    for k in (1, 5, 16, 32, 40):
+        s = GS().setInputCloud(ref, k_hint=k)
+        gi, gd, _ = s.nearestKSearch(qry, k)
+        oi, od, _ = tree.knn(qry, k)
+        assert_knn_equal(gi, gd, oi, od)
+    # radius: pick r so rows hold ~20 neighbours on average
+    _, d2_20, _ = tree.knn(qry[:200], 20)
+    r = float(np.sqrt(np.median(d2_20[:, -1])))
+    s = GS().setInputCloud(ref, cell_hint=r)
+    off, idx, d2 = s.radiusSearch(qry, r)
+    ooff, oidx, od2 = tree.radius(qry, r)
+    assert np.array_equal(off, ooff) and np.array_equal(idx, oidx) and np.array_equal(bits(d2), bits(od2))
+    md = GS().setInputCloud(ref, k_hint=9).meanNeighbourDistance(None, 8)
+    assert np.array_equal(bits(md), bits(oracle.sor(ref, 8, 1.0, tree=tree)["distances"]))
