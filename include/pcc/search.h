@@ -115,6 +115,19 @@ int pcc_umeyama_from_sums(const double sums[16], int64_t count, float T16[16]);
 int pcc_euclidean_labels(pcc_index *idx, double tolerance, int64_t min_size, int64_t max_size, int32_t *labels,
                          int64_t *n_clusters, int64_t *sizes, int64_t sizes_cap, int mem, void *stream);
 
+/* Sharded clustering for query-sharded multi-GPU runs.  Forests are uint32[pcc_size] arrays over
+ * SORTED positions in device memory (the grid is replicated, so positions mean the same on every rank):
+ *   pcc_ece_init        parent[i] = i
+ *   pcc_ece_link_range  hook the radius-graph edges whose query endpoint is in [begin, end) (this rank's shard)
+ *   pcc_ece_absorb      unite i with other[i] for every i (other = the element-wise MIN all-reduce of the ranks' compressed
+ *                       forests), then compress so parent[i] = root = smallest member; repeat until the all-reduce is a fix-point
+ *   pcc_ece_finish      sizes, size filter, PCL ordering, labels[n_input] in ORIGINAL row order (device pointers) */
+int pcc_ece_init(pcc_index *idx, uint32_t *parent, void *stream);
+int pcc_ece_link_range(pcc_index *idx, double tolerance, int64_t begin, int64_t end, uint32_t *parent, void *stream);
+int pcc_ece_absorb(pcc_index *idx, const uint32_t *other, uint32_t *parent, void *stream);
+int pcc_ece_finish(pcc_index *idx, uint32_t *parent, int64_t min_size, int64_t max_size, int32_t *labels, int64_t *n_clusters, int64_t *sizes,
+                   int64_t sizes_cap, void *stream);
+
 /* SIFT keypoint -> first cloud point within `thr` in index order (src/comparator.cpp:696-713):
  * out[i] = lowest original index with sqrt(double(dx)^2+double(dy)^2+double(dz)^2) < thr, or -1. */
 int pcc_first_within(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, double thr, int32_t *out, int mem, void *stream);

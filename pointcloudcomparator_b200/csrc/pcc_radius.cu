@@ -132,6 +132,24 @@ __global__ void __launch_bounds__(128) ece_link_kernel(Grid g, float r2, int R0,
     const float4 q = __ldg(g.pts + t);
     radius_visit(g, q.x, q.y, q.z, r2, R0, [&](uint32_t pos, float4, float) { if (pos < (uint32_t)t) uf_union(parent, (uint32_t)t, pos); });
 }
+// sharded clustering: link only the edges whose query endpoint lies in [begin, end) of the sorted order
+__global__ void __launch_bounds__(128) ece_link_range_kernel(Grid g, float r2, int R0, uint32_t begin, uint32_t end, uint32_t *__restrict__ parent) {
+    const int64_t t = (int64_t)begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= end) return;
+    const float4 q = __ldg(g.pts + t);
+    radius_visit(g, q.x, q.y, q.z, r2, R0, [&](uint32_t pos, float4, float) { if (pos != (uint32_t)t) uf_union(parent, (uint32_t)t, pos); });
+}
+// merge another rank's knowledge: node i and other[i] are in the same component
+__global__ void ece_absorb_kernel(uint32_t n, const uint32_t *__restrict__ other, uint32_t *__restrict__ parent) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t o = other[t];
+    if (o != (uint32_t)t && o < n) uf_union(parent, (uint32_t)t, o);
+}
+__global__ void ece_compress_kernel(uint32_t n, uint32_t *__restrict__ parent) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) parent[t] = uf_find(parent, (uint32_t)t);
+}
 __global__ void ece_flatten_kernel(Grid g, uint32_t *__restrict__ parent, uint32_t *__restrict__ size, uint32_t *__restrict__ min_orig) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= g.n) return;
@@ -342,36 +360,28 @@ int pcc_first_within(pcc_index *idx, const void *q, int64_t nq, int stride_bytes
     return PCC_OK;
 }
 
-int pcc_euclidean_labels(pcc_index *idx, double tolerance, int64_t min_size, int64_t max_size, int32_t *labels, int64_t *n_clusters, int64_t *sizes,
-                         int64_t sizes_cap, int mem, void *stream) {
-    PCC_TRY(check_common(idx));
-    if (!(tolerance >= 0) || !labels || !n_clusters) return fail(PCC_ERR_INVALID, "bad tolerance / outputs");
-    cudaStream_t s = (cudaStream_t)stream;
+// sizes, PCL ordering and labels from a parent forest over sorted positions (any forest whose trees are the components)
+static int ece_finish(pcc_index *idx, uint32_t *parent, int64_t min_size, int64_t max_size, int32_t *labels, int64_t *n_clusters, int64_t *sizes,
+                      int64_t sizes_cap, int mem, cudaStream_t s) {
     const int64_t n = idx->n_indexed, rows = idx->n_input;
-    *n_clusters = 0;
-    if (rows == 0) return PCC_OK;
     int32_t *d_labels = labels;
     if (mem == PCC_HOST) { PCC_TRY(idx->out_i.reserve((size_t)rows * 4)); d_labels = idx->out_i.as<int32_t>(); }
     PCC_CUDA(cudaMemsetAsync(d_labels, 0xFF, (size_t)rows * 4, s));
     int64_t kept = 0;
     int64_t *d_sizes = sizes;
     if (n > 0) {
-        const float r2 = (float)(tolerance * tolerance);
         const Grid g = idx->grid();
-        // parent | size | min_orig | rank_of_root | roots | roots_sorted : 6 x uint32[n]; keys | keys_sorted : 2 x u64[n]
-        PCC_TRY(idx->parent.reserve((size_t)n * 4 * 6));
+        // size | min_orig | rank_of_root | roots | roots_sorted : 5 x uint32[n]; keys | keys_sorted : 2 x u64[n]
+        PCC_TRY(idx->misc.reserve((size_t)n * 4 * 5));
         PCC_TRY(idx->keys64.reserve((size_t)n * 8 + 64)); PCC_TRY(idx->keys64b.reserve((size_t)n * 8));
-        uint32_t *parent = idx->parent.as<uint32_t>(), *size = parent + n, *min_orig = size + n, *rank_of_root = min_orig + n, *roots = rank_of_root + n, *roots_sorted = roots + n;
+        uint32_t *size = idx->misc.as<uint32_t>(), *min_orig = size + n, *rank_of_root = min_orig + n, *roots = rank_of_root + n, *roots_sorted = roots + n;
         nkey_t *keys = idx->keys64.as<nkey_t>(), *keys_sorted = idx->keys64b.as<nkey_t>();
         unsigned long long *d_kept = (unsigned long long *)(keys + n);
-        const unsigned nb = nblocks(n, 128), nb256 = nblocks(n, 256);
-        KernelTimer timer(idx, s);
-        iota_kernel<<<nb256, 256, 0, s>>>(parent, n); PCC_LAUNCHED();
+        const unsigned nb256 = nblocks(n, 256);
         PCC_CUDA(cudaMemsetAsync(size, 0, (size_t)n * 4, s));
         PCC_CUDA(cudaMemsetAsync(min_orig, 0xFF, (size_t)n * 4, s));
         PCC_CUDA(cudaMemsetAsync(rank_of_root, 0xFF, (size_t)n * 4, s));
         PCC_CUDA(cudaMemsetAsync(d_kept, 0, 8, s));
-        ece_link_kernel<<<nb, 128, 0, s>>>(g, r2, ring0(idx, tolerance), parent); PCC_LAUNCHED();
         ece_flatten_kernel<<<nb256, 256, 0, s>>>(g, parent, size, min_orig); PCC_LAUNCHED();
         const uint32_t mn = (uint32_t)std::min<int64_t>(std::max<int64_t>(min_size, 0), 0xFFFFFFFFll), mxs = (uint32_t)std::min<int64_t>(std::max<int64_t>(max_size, 0), 0xFFFFFFFFll);
         ece_select_kernel<<<nb256, 256, 0, s>>>((uint32_t)n, parent, size, min_orig, mn, mxs, keys, roots, d_kept); PCC_LAUNCHED();
@@ -391,7 +401,6 @@ int pcc_euclidean_labels(pcc_index *idx, double tolerance, int64_t min_size, int
         }
         ece_label_kernel<<<nb256, 256, 0, s>>>(g, parent, rank_of_root, d_labels); PCC_LAUNCHED();
         PCC_CUDA(cudaGetLastError());
-        timer.stop();
     }
     if (mem == PCC_HOST) {
         PCC_TRY(copy_out(labels, d_labels, (size_t)rows * 4, mem, s));
@@ -400,6 +409,61 @@ int pcc_euclidean_labels(pcc_index *idx, double tolerance, int64_t min_size, int
     PCC_CUDA(cudaStreamSynchronize(s));
     *n_clusters = kept;
     return PCC_OK;
+}
+
+int pcc_euclidean_labels(pcc_index *idx, double tolerance, int64_t min_size, int64_t max_size, int32_t *labels, int64_t *n_clusters, int64_t *sizes,
+                         int64_t sizes_cap, int mem, void *stream) {
+    PCC_TRY(check_common(idx));
+    if (!(tolerance >= 0) || !labels || !n_clusters) return fail(PCC_ERR_INVALID, "bad tolerance / outputs");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n = idx->n_indexed;
+    *n_clusters = 0;
+    if (idx->n_input == 0) return PCC_OK;
+    PCC_TRY(idx->parent.reserve((size_t)std::max<int64_t>(n, 1) * 4));
+    uint32_t *parent = idx->parent.as<uint32_t>();
+    KernelTimer timer(idx, s);
+    if (n > 0) {
+        iota_kernel<<<nblocks(n, 256), 256, 0, s>>>(parent, n); PCC_LAUNCHED();
+        ece_link_kernel<<<nblocks(n, 128), 128, 0, s>>>(idx->grid(), (float)(tolerance * tolerance), ring0(idx, tolerance), parent); PCC_LAUNCHED();
+        PCC_CUDA(cudaGetLastError());
+    }
+    const int rc = ece_finish(idx, parent, min_size, max_size, labels, n_clusters, sizes, sizes_cap, mem, s);
+    timer.stop();
+    return rc;
+}
+
+// ---- sharded clustering: parent forests over SORTED positions, device memory only ----
+int pcc_ece_init(pcc_index *idx, uint32_t *parent, void *stream) {
+    PCC_TRY(check_common(idx));
+    if (!parent) return fail(PCC_ERR_INVALID, "parent is NULL");
+    if (idx->n_indexed > 0) { iota_kernel<<<nblocks(idx->n_indexed, 256), 256, 0, (cudaStream_t)stream>>>(parent, idx->n_indexed); PCC_LAUNCHED(); PCC_CUDA(cudaGetLastError()); }
+    return PCC_OK;
+}
+int pcc_ece_link_range(pcc_index *idx, double tolerance, int64_t begin, int64_t end, uint32_t *parent, void *stream) {
+    PCC_TRY(check_common(idx));
+    if (!(tolerance >= 0) || !parent || begin < 0 || end > idx->n_indexed || begin > end) return fail(PCC_ERR_INVALID, "bad range [%lld, %lld) of %lld", (long long)begin, (long long)end, (long long)idx->n_indexed);
+    if (end > begin) {
+        ece_link_range_kernel<<<nblocks(end - begin, 128), 128, 0, (cudaStream_t)stream>>>(idx->grid(), (float)(tolerance * tolerance), ring0(idx, tolerance), (uint32_t)begin, (uint32_t)end, parent);
+        PCC_LAUNCHED(); PCC_CUDA(cudaGetLastError());
+    }
+    return PCC_OK;
+}
+int pcc_ece_absorb(pcc_index *idx, const uint32_t *other, uint32_t *parent, void *stream) {
+    PCC_TRY(check_common(idx));
+    if (!other || !parent) return fail(PCC_ERR_INVALID, "NULL forest");
+    if (idx->n_indexed > 0) {
+        ece_absorb_kernel<<<nblocks(idx->n_indexed, 256), 256, 0, (cudaStream_t)stream>>>((uint32_t)idx->n_indexed, other, parent); PCC_LAUNCHED();
+        ece_compress_kernel<<<nblocks(idx->n_indexed, 256), 256, 0, (cudaStream_t)stream>>>((uint32_t)idx->n_indexed, parent); PCC_LAUNCHED();
+        PCC_CUDA(cudaGetLastError());
+    }
+    return PCC_OK;
+}
+int pcc_ece_finish(pcc_index *idx, uint32_t *parent, int64_t min_size, int64_t max_size, int32_t *labels, int64_t *n_clusters, int64_t *sizes, int64_t sizes_cap, void *stream) {
+    PCC_TRY(check_common(idx));
+    if (!parent || !labels || !n_clusters) return fail(PCC_ERR_INVALID, "NULL argument");
+    *n_clusters = 0;
+    if (idx->n_input == 0) return PCC_OK;
+    return ece_finish(idx, parent, min_size, max_size, labels, n_clusters, sizes, sizes_cap, PCC_DEVICE, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -200,6 +200,26 @@ class GridSearch:
         check(self._L.pcc_euclidean_labels(self._h, float(tolerance), int(min_size), int(max_size), lp, C.byref(nc), sp, cap, mem, _stream()))
         return labels[: self._n_input], sizes[: nc.value]
 
+    # ---- sharded clustering primitives (device tensors; forests over SORTED positions, see include/pcc/search.h) ----
+    def eceNewForest(self):
+        parent = torch.empty(max(self.size, 1), dtype=torch.int32, device=f"cuda:{self.device}")
+        check(self._L.pcc_ece_init(self._h, parent.data_ptr(), _stream()))
+        return parent
+
+    def eceLinkRange(self, parent, tolerance: float, begin: int, end: int):
+        check(self._L.pcc_ece_link_range(self._h, float(tolerance), int(begin), int(end), parent.data_ptr(), _stream()))
+
+    def eceAbsorb(self, parent, other):
+        check(self._L.pcc_ece_absorb(self._h, other.data_ptr(), parent.data_ptr(), _stream()))
+
+    def eceFinish(self, parent, min_size: int = 1, max_size: int = 2**31 - 1):
+        labels = torch.empty(max(self._n_input, 1), dtype=torch.int32, device=f"cuda:{self.device}")
+        cap = max(self._n_input // max(int(min_size), 1) + 1, 1)
+        sizes = torch.empty(cap, dtype=torch.int64, device=f"cuda:{self.device}")
+        nc = C.c_int64()
+        check(self._L.pcc_ece_finish(self._h, parent.data_ptr(), int(min_size), int(max_size), labels.data_ptr(), C.byref(nc), sizes.data_ptr(), cap, _stream()))
+        return labels[: self._n_input], sizes[: nc.value]
+
     def firstWithin(self, queries, thr: float):
         ptr, nq, stride, mem, keep = _rows(queries)
         out, op = self._alloc(mem, (nq,), np.int32)

@@ -110,6 +110,29 @@ def merge_labels_min(labels: "torch.Tensor", edges_a: "torch.Tensor", edges_b: "
     return lab
 
 
+def euclidean_clusters_sharded(search, tolerance: float, min_size: int, max_size: int, group=None, max_rounds: int = 64):
+    """EuclideanClusterExtraction with the radius-graph work sharded over the ranks (replicated grid).
+
+    Each rank links only the edges whose query endpoint lies in its contiguous range of the sorted order
+    (`pcc_ece_link_range`), then the ranks repeat {element-wise MIN all-reduce of the compressed forests (NCCL),
+    absorb the result (`pcc_ece_absorb`)} until the all-reduce is a fix-point -- typically 2-3 rounds.  Every rank ends
+    with the same forest and finishes locally (sizes, size filter, PCL ordering).  Returns (labels[n_input], sizes)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    b, e = shard_ranges(search.size, world)[rank]
+    parent = search.eceNewForest()
+    search.eceLinkRange(parent, tolerance, b, e)
+    search.eceAbsorb(parent, parent)                       # compress: parent[i] = root = smallest member
+    for _ in range(max_rounds):
+        merged = parent.clone()
+        dist.all_reduce(merged, op=dist.ReduceOp.MIN, group=group)
+        changed = torch.tensor([0 if torch.equal(merged, parent) else 1], dtype=torch.int32, device=parent.device)
+        dist.all_reduce(changed, op=dist.ReduceOp.MAX, group=group)
+        if int(changed.item()) == 0:
+            break
+        search.eceAbsorb(parent, merged)
+    return search.eceFinish(parent, min_size, max_size)
+
+
 def broadcast_grid(search, src: int = 0, group=None):
     """Rank `src` has a built GridSearch; every other rank adopts its grid (meta via broadcast_object_list,
     the float4 points and the cell-start table via NCCL broadcast straight into the adopted device arrays)."""

@@ -344,3 +344,31 @@ def test_randomized_stress_knn_and_radius(GS, kind):
     assert np.array_equal(off, ooff) and np.array_equal(idx, oidx) and np.array_equal(bits(d2), bits(od2))
     md = GS().setInputCloud(ref, k_hint=9).meanNeighbourDistance(None, 8)
     assert np.array_equal(bits(md), bits(oracle.sor(ref, 8, 1.0, tree=tree)["distances"]))
+
+
+def test_sharded_clustering_two_emulated_ranks(GS):
+    """pcc_ece_link_range / absorb / finish with two ranks emulated in one process (sequential kernels over both ranks'
+    forests; the element-wise MIN stands in for the NCCL all-reduce of shard.euclidean_clusters_sharded)."""
+    import torch
+    pts, ids = synth.scene(300000, 3001, extent=10.0, n_objects=60)
+    s = GS().setInputCloud(torch.from_numpy(pts).cuda(), cell_hint=0.05)
+    n = s.size
+    ranges = [(0, n // 3), (n // 3, n)]                                       # uneven shards
+    forests = []
+    for b, e in ranges:
+        f = s.eceNewForest(); s.eceLinkRange(f, 0.05, b, e); s.eceAbsorb(f, f); forests.append(f)
+    assert not torch.equal(forests[0], forests[1])
+    rounds = 0
+    while True:
+        merged = torch.minimum(forests[0], forests[1])
+        if all(torch.equal(merged, f) for f in forests):
+            break
+        for f in forests:
+            s.eceAbsorb(f, merged)
+        rounds += 1
+        assert rounds < 20
+    lab, sizes = s.eceFinish(forests[0], 100, 250000)
+    olab, osizes = oracle.KdTree(pts).ece(0.05, 100, 250000)
+    assert np.array_equal(lab.cpu().numpy(), olab) and np.array_equal(sizes.cpu().numpy(), osizes)
+    lab1, sizes1 = s.eceFinish(forests[1], 100, 250000)
+    assert torch.equal(lab, lab1) and torch.equal(sizes, sizes1)
