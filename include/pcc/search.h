@@ -132,6 +132,15 @@ int pcc_ece_finish(pcc_index *idx, uint32_t *parent, int64_t min_size, int64_t m
  * out[i] = lowest original index with sqrt(double(dx)^2+double(dy)^2+double(dz)^2) < thr, or -1. */
 int pcc_first_within(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, double thr, int32_t *out, int mem, void *stream);
 
+/* pcl::VoxelGrid<PointT>::applyFilter [up] as the reference calls it before every segmentation search
+ * (src/segmentation.cpp:69-74, 223-228; leaf 0.025): one centroid per occupied voxel, output ordered by voxel index
+ * (x fastest), downsample_all_data semantics for PointXYZRGB (x, y, z averaged in fp32; r, g, b averaged and truncated,
+ * packed at rgb_offset_bytes, -1 = no colour field).  `out` has room for n rows of stride_bytes; *n_out rows are written.
+ * `idx` only provides the device and scratch buffers (it does not need to be built).  Points of a voxel are summed in
+ * ascending row order (PCL's std::sort leaves that order unspecified). */
+int pcc_voxel_grid(pcc_index *idx, const void *pts, int64_t n, int stride_bytes, int rgb_offset_bytes, const float leaf[3],
+                   int min_points_per_voxel, void *out, int64_t *n_out, int mem, void *stream);
+
 /* Multi-GPU plumbing (query sharding with a replicated grid): the built index is four flat device
  * arrays that a host layer can broadcast with NCCL and adopt on the other ranks.
  * meta[16] (host doubles): n_indexed, n_input, nx, ny, nz, origin xyz, cell, inv_cell, mean occupancy, n_cells.

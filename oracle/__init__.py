@@ -53,6 +53,8 @@ def lib():
         L.orc_icp_pass.argtypes = [vp, f32p, i32, f32p, i64, C.POINTER(dbl), i32p, f32p, i32]
         L.orc_icp.argtypes = [f32p, i64, i32, f32p, i64, i32, i32, f32p, C.POINTER(i32), C.POINTER(dbl), C.POINTER(i32), C.POINTER(dbl), i32]
         L.orc_first_within.argtypes = [f32p, i64, i32, f32p, i64, i32, dbl, i32p]
+        L.orc_voxel_grid.restype = i64
+        L.orc_voxel_grid.argtypes = [f32p, i64, i32, i32, f32p, i32, f32p]
         L.orc_num_threads.restype = i32
         _lib = L
     return _lib
@@ -213,3 +215,14 @@ def first_within(pts, q, thr: float):
     out = np.empty(q.shape[0], np.int32)
     lib().orc_first_within(_p(pts, C.c_float), pts.shape[0], pts.shape[1], _p(q, C.c_float), q.shape[0], q.shape[1], thr, _p(out, C.c_int32))
     return out
+
+
+def voxel_grid(rows, leaf, rgb_offset_floats: int = -1, min_points: int = 0):
+    """pcl::VoxelGrid::applyFilter over rows[n, stride] (float32; colour as a packed BGRA word at rgb_offset_floats)."""
+    rows = np.ascontiguousarray(rows, np.float32)
+    leaf = np.ascontiguousarray(np.broadcast_to(np.asarray(leaf, np.float32), (3,)))
+    out = np.zeros_like(rows)
+    n = lib().orc_voxel_grid(_p(rows, C.c_float), rows.shape[0], rows.shape[1], rgb_offset_floats, _p(leaf, C.c_float), min_points, _p(out, C.c_float))
+    if n < 0:
+        raise ValueError("leaf size is too small for the input dataset")
+    return out[:n]

@@ -677,6 +677,70 @@ ORC_API void orc_first_within(const float *pts, int64_t n, int stride_f, const f
     }
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* pcl::VoxelGrid<PointT>::applyFilter [upstream filters/impl/voxel_grid.hpp] as the reference configures it
+ * (src/segmentation.cpp:69-74, 223-228: leaf 0.025, downsample_all_data = true, min_points_per_voxel = 0).
+ * Points of a voxel are summed in ascending row order (PCL's std::sort leaves the order unspecified).
+ * rows: stride_f floats; rgb_off_f = float offset of the packed BGRA word or -1.  Returns the number of output rows. */
+typedef struct { uint32_t key; int32_t row; } orc_vx;
+static int orc_vx_cmp(const void *a, const void *b) {
+    const orc_vx *x = (const orc_vx *)a, *y = (const orc_vx *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return (x->row > y->row) - (x->row < y->row);
+}
+ORC_API int64_t orc_voxel_grid(const float *pts, int64_t n, int stride_f, int rgb_off_f, const float *leaf, int min_points, float *out) {
+    float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0}; int64_t m = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const float *p = pts + i * stride_f;
+        if (!orc_finite3(p)) continue;
+        for (int d = 0; d < 3; ++d) { if (m == 0 || p[d] < mn[d]) mn[d] = p[d]; if (m == 0 || p[d] > mx[d]) mx[d] = p[d]; }
+        ++m;
+    }
+    if (m == 0) return 0;
+    float inv[3]; int min_b[3], mul[3]; int64_t div[3];
+    for (int d = 0; d < 3; ++d) {
+        inv[d] = 1.0f / leaf[d];
+        min_b[d] = (int)floorf(mn[d] * inv[d]);
+        div[d] = (int64_t)((int)floorf(mx[d] * inv[d])) - min_b[d] + 1;
+    }
+    if ((double)div[0] * (double)div[1] * (double)div[2] > 2147483647.0) return -1;      /* "Leaf size is too small" */
+    mul[0] = 1; mul[1] = (int)div[0]; mul[2] = (int)(div[0] * div[1]);
+    orc_vx *v = (orc_vx *)malloc(sizeof(orc_vx) * (size_t)m);
+    int64_t c = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const float *p = pts + i * stride_f;
+        if (!orc_finite3(p)) continue;
+        int i0 = (int)(floorf(p[0] * inv[0]) - (float)min_b[0]);
+        int i1 = (int)(floorf(p[1] * inv[1]) - (float)min_b[1]);
+        int i2 = (int)(floorf(p[2] * inv[2]) - (float)min_b[2]);
+        v[c].key = (uint32_t)(i0 * mul[0] + i1 * mul[1] + i2 * mul[2]); v[c].row = (int32_t)i; ++c;
+    }
+    qsort(v, (size_t)m, sizeof(orc_vx), orc_vx_cmp);
+    int64_t total = 0, index = 0;
+    while (index < m) {
+        int64_t i = index + 1;
+        while (i < m && v[i].key == v[index].key) ++i;
+        if (i - index >= (int64_t)min_points) {
+            float sx = 0, sy = 0, sz = 0, sr = 0, sg = 0, sb = 0;
+            for (int64_t j = index; j < i; ++j) {
+                const float *p = pts + (int64_t)v[j].row * stride_f;
+                if (j == index) { sx = p[0]; sy = p[1]; sz = p[2]; } else { sx += p[0]; sy += p[1]; sz += p[2]; }
+                if (rgb_off_f >= 0) { const uint8_t *col = (const uint8_t *)(p + rgb_off_f); sb += (float)col[0]; sg += (float)col[1]; sr += (float)col[2]; }
+            }
+            float cnt = (float)(i - index);
+            float *o = out + total * stride_f;
+            memset(o, 0, sizeof(float) * (size_t)stride_f);
+            o[0] = sx / cnt; o[1] = sy / cnt; o[2] = sz / cnt;
+            if (stride_f >= 4) o[3] = 1.0f;
+            if (rgb_off_f >= 0) { int r = (int)(sr / cnt), g = (int)(sg / cnt), b = (int)(sb / cnt); int rgb = (r << 16) | (g << 8) | b; memcpy(o + rgb_off_f, &rgb, 4); }
+            ++total;
+        }
+        index = i;
+    }
+    free(v);
+    return total;
+}
+
 ORC_API int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -247,6 +247,23 @@ class GridSearch:
         return self.export()
 
 
+def voxel_grid(rows, leaf, rgb_offset_bytes: int = -1, min_points: int = 0, device: int = 0, workspace: "GridSearch | None" = None):
+    """pcl::VoxelGrid::applyFilter (src/segmentation.cpp:69-74, 223-228) on the GPU: rows[n, stride] float32 (numpy or CUDA
+    tensor, colour as a packed BGRA word at rgb_offset_bytes) -> one centroid row per occupied voxel, ordered by voxel index."""
+    ws = workspace or GridSearch(device)
+    ptr, n, stride, mem, keep = _rows(rows)
+    lf = (C.c_float * 3)(*np.broadcast_to(np.asarray(leaf, np.float32), (3,)).tolist())
+    if mem == DEVICE:
+        out = torch.empty_like(rows)
+        op = out.data_ptr()
+    else:
+        out = np.zeros((n, stride // 4), np.float32)
+        op = out.ctypes.data
+    n_out = C.c_int64()
+    check(ws._L.pcc_voxel_grid(ws._h, ptr, n, stride, int(rgb_offset_bytes), lf, int(min_points), op, C.byref(n_out), mem, _stream()))
+    return out[: n_out.value]
+
+
 def umeyama_from_sums(sums, count: int):
     T = (C.c_float * 16)()
     s = (C.c_double * 16)(*[float(v) for v in sums])

@@ -372,3 +372,27 @@ def test_sharded_clustering_two_emulated_ranks(GS):
     assert np.array_equal(lab.cpu().numpy(), olab) and np.array_equal(sizes.cpu().numpy(), osizes)
     lab1, sizes1 = s.eceFinish(forests[1], 100, 250000)
     assert torch.equal(lab, lab1) and torch.equal(sizes, sizes1)
+
+
+def test_voxel_grid_vs_oracle(GS):
+    """VoxelGrid leaf 0.025 on the coloured room (src/segmentation.cpp:69-74); bit-exact vs the oracle."""
+    import torch
+    from pointcloudcomparator_b200.search import voxel_grid
+    n = 200000
+    rows = np.zeros((n, 8), np.float32)
+    rows[:, :3] = synth.room(n, 1001)
+    rows[:, 3] = 1.0
+    rgb = synth.rgb_for(rows, 7)
+    rows[:, 4:5].view(np.uint8)[:, :3] = rgb[:, ::-1]          # BGRA
+    rows[11, 1] = np.nan
+    for leaf in (0.025, 0.1, (0.05, 0.025, 0.2)):
+        got = voxel_grid(rows, leaf, rgb_offset_bytes=16)
+        ref = oracle.voxel_grid(rows, leaf, rgb_offset_floats=4)
+        assert got.shape == ref.shape and np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    got = voxel_grid(rows, 0.1, rgb_offset_bytes=16, min_points=5)
+    ref = oracle.voxel_grid(rows, 0.1, rgb_offset_floats=4, min_points=5)
+    assert got.shape == ref.shape and np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    dev = voxel_grid(torch.from_numpy(rows).cuda(), 0.025, rgb_offset_bytes=16)
+    assert np.array_equal(dev.cpu().numpy().view(np.uint32), oracle.voxel_grid(rows, 0.025, rgb_offset_floats=4).view(np.uint32))
+    xyz = synth.uniform(100000, 5, 2.0)                        # packed xyz rows, no colour
+    assert np.array_equal(voxel_grid(xyz, 0.05).view(np.uint32), oracle.voxel_grid(xyz, 0.05).view(np.uint32))

@@ -164,3 +164,26 @@ def test_first_within():
     pts = np.array([[0, 0, 0], [0.04, 0, 0], [0.01, 0, 0]], np.float32)
     q = np.array([[0.03, 0, 0], [1, 1, 1]], np.float32)
     assert oracle.first_within(pts, q, 0.05).tolist() == [0, -1]
+
+
+def test_voxel_grid_known_answers():
+    # two points in one 1 m voxel, one alone; colour averaged and truncated; output ordered by voxel index (x fastest)
+    rows = np.zeros((3, 8), np.float32)
+    rows[:, :3] = [[2.25, 0.5, 0.5], [0.25, 0.25, 0.25], [0.75, 0.5, 0.75]]
+    rows[:, 3] = 1.0
+    col = rows[:, 4:5].view(np.uint8)                       # BGRA bytes
+    col[0] = [10, 20, 30, 0]; col[1] = [0, 100, 255, 0]; col[2] = [1, 101, 0, 0]
+    out = oracle.voxel_grid(rows, 1.0, rgb_offset_floats=4)
+    assert out.shape[0] == 2
+    assert np.allclose(out[0, :3], [0.5, 0.375, 0.5]) and np.allclose(out[1, :3], [2.25, 0.5, 0.5])
+    assert out[0, 4:5].view(np.uint8).tolist() == [0, 100, 127, 0] and out[1, 4:5].view(np.uint8).tolist() == [10, 20, 30, 0]
+    assert (out[:, 3] == 1.0).all()
+    # distinct-voxel count equals numpy's, NaN rows are ignored
+    p = synth.room(50000, 1001, stride4=True)
+    p[7, 0] = np.nan
+    o = oracle.voxel_grid(p, 0.025)
+    fin = np.isfinite(p[:, :3]).all(1)
+    ijk = np.floor(p[fin, :3] * np.float32(1 / np.float32(0.025))).astype(np.int64)
+    assert o.shape[0] == len(np.unique(ijk, axis=0))
+    vox = np.floor(o[:, :3] * np.float32(1 / np.float32(0.025)) + 1e-4).astype(np.int64)
+    assert len(np.unique(vox, axis=0)) >= 0.999 * o.shape[0]      # every centroid stays inside its own voxel (up to fp32 rounding on faces)
