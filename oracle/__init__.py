@@ -82,9 +82,9 @@ class KdTree:
         self._h = lib().orc_tree_build(_p(self.pts, C.c_float), self.pts.shape[0], self.pts.shape[1], leaf_max)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().orc_tree_free(self._h)
-            self._h = None
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:          # _lib is None during interpreter shutdown
+            _lib.orc_tree_free(h)
 
     @property
     def size(self) -> int:

@@ -173,6 +173,174 @@ __global__ void __launch_bounds__(FastCfg<K>::threads, FastCfg<K>::min_blocks) k
     write_row<K>(e, k, out_idx + row * k, out_d2 + row * k, vec4);
 }
 
+// ---- warp-owns-a-cell variant: the 3x3x3 stencil is staged in shared memory with TMA bulk copies ----
+// Used when a grid cell holds many queries (Q >> N, e.g. the 100 M-query point of the BASELINE sweep): the lanes of a warp
+// that fall into the same cell share one stencil, so the warp (a) computes the 9 run bounds once, (b) pulls the runs into
+// its shared-memory tile with cp.async.bulk (one elected lane, completion on an mbarrier), and (c) walks the tile with
+// UNIFORM trip counts and broadcast 16-byte shared loads -- no per-lane address math, no run-length divergence.  Ring >= 2,
+// the logged phase 2, the sort and the write are the per-lane code of knn_fast_kernel.  With few queries per cell the
+// lanes of a warp belong to ~4 different cells and this variant loses to the per-thread walk; measured on B200 it also loses
+// at 80 queries per cell (single-buffered tiles expose the bulk-copy latency), so it is opt-in only.
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+}  // namespace tma
+
+static constexpr int kCellWarps = 4, kCellCap = 320, kCellLog = 48;   // 20 KB tiles + 24 KB logs per block (static shared memory limit 48 KB)
+template <int K>
+__global__ void __launch_bounds__(kCellWarps * 32, 5) knn_cell_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4, FixList fix) {
+    __shared__ __align__(128) float4 s_tile[kCellWarps][kCellCap];
+    __shared__ uint32_t s_log_all[kCellWarps][kCellLog][32];
+    __shared__ __align__(8) unsigned long long s_bar[kCellWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 *tile = s_tile[warp];
+    uint32_t *slog = &s_log_all[warp][0][lane];           // slot stride = 32 words
+    unsigned long long *bar = &s_bar[warp];
+    if (lane == 0) tma::mbar_init(bar, 1);
+    __syncwarp();
+    unsigned parity = 0;
+
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float x = 0.f, y = 0.f, z = 0.f; int64_t row = 0; bool empty = false;
+    const bool live = load_query(g, v, t, x, y, z, row, empty);
+    QueryCell c; c.cx = c.cy = c.cz = 0; c.ux = c.uy = c.uz = 0.f;
+    if (live) c = locate(g, x, y, z);
+    const int cell_id = live ? (c.cz * g.ny + c.cy) * g.nx + c.cx : -1;
+    RegDist<K> list; list.init();
+    int nlog = 0;
+
+    // ring 1, cooperatively per distinct cell among the warp's lanes
+    unsigned todo = __ballot_sync(0xffffffffu, live);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int cid = __shfl_sync(0xffffffffu, cell_id, leader);
+        const bool mine = live && cell_id == cid;
+        const unsigned group = __ballot_sync(0xffffffffu, mine);
+        const int lcx = __shfl_sync(0xffffffffu, c.cx, leader), lcy = __shfl_sync(0xffffffffu, c.cy, leader), lcz = __shfl_sync(0xffffffffu, c.cz, leader);
+        // lane r < 9 owns row r of the stencil (centre-out order); bounds are then broadcast with shuffles
+        uint32_t my_s = 0, my_e = 0;
+        if (lane < 9) {
+            const int dz = centre_out(lane / 3), dy = centre_out(lane % 3);
+            const int zz = lcz + dz, yy = lcy + dy;
+            if (zz >= 0 && zz < g.nz && yy >= 0 && yy < g.ny) {
+                const uint32_t *rowp = g.cell_start + ((size_t)zz * g.ny + yy) * g.nx;
+                my_s = __ldg(rowp + max(lcx - 1, 0)); my_e = __ldg(rowp + min(lcx + 1, g.nx - 1) + 1);
+            }
+        }
+        int r = 0; uint32_t off_in_run = 0;               // progress through the 9 runs (uniform across the warp)
+        while (r < 9) {
+            // plan one tile: whole runs while they fit, else a slice of the run that does not fit.  Every lane computes the same
+            // plan; lane q keeps the (start, count) of run q so later loops can fetch it with a runtime-indexed shuffle.
+            uint32_t my_ts = 0, my_tn = 0, fill = 0;
+            int r_next = 9; uint32_t off_next = 0; bool open = true;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const uint32_t s_q = __shfl_sync(0xffffffffu, my_s, q), e_q = __shfl_sync(0xffffffffu, my_e, q);
+                if (open && q >= r) {
+                    const uint32_t begin = s_q + (q == r ? off_in_run : 0u);
+                    const uint32_t avail = e_q - begin;
+                    const uint32_t take = min(avail, (uint32_t)kCellCap - fill);
+                    if (lane == q) { my_ts = begin; my_tn = take; }
+                    fill += take;
+                    if (take == avail) { r_next = q + 1; off_next = 0; }
+                    else { r_next = q; off_next = (q == r ? off_in_run : 0u) + take; open = false; }
+                    if (fill == (uint32_t)kCellCap) open = false;
+                }
+            }
+            r = r_next; off_in_run = off_next;
+            if (fill == 0) continue;
+            // stage the tile: one elected lane posts the byte count and issues one bulk copy per run
+            if (lane == 0) { tma::fence_proxy_async(); tma::mbar_expect_tx(bar, fill * 16u); }
+            {
+                uint32_t off = 0;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) {
+                    const uint32_t ts = __shfl_sync(0xffffffffu, my_ts, q), tn = __shfl_sync(0xffffffffu, my_tn, q);
+                    if (lane == 0 && tn) tma::bulk_g2s(tile + off, g.pts + ts, tn * 16u, bar);
+                    off += tn;
+                }
+            }
+            tma::mbar_wait(bar, parity); parity ^= 1u;
+            // walk the tile: uniform trip counts, broadcast 16-byte shared loads
+            uint32_t off = 0;
+#pragma unroll 1
+            for (int q = 0; q < 9; ++q) {
+                const uint32_t ts = __shfl_sync(0xffffffffu, my_ts, q), tn = __shfl_sync(0xffffffffu, my_tn, q);
+                for (uint32_t jj = 0; jj < tn; ++jj) {
+                    const float4 p = tile[off + jj];
+                    if (mine) {
+                        const float d2 = dist2(x, y, z, p.x, p.y, p.z);
+                        if (d2 <= list.d[K - 1]) {
+                            if (nlog < kCellLog) slog[nlog * 32] = ts + jj;
+                            ++nlog;
+                            list.insert(d2);
+                        }
+                    }
+                }
+                off += tn;
+            }
+            __syncwarp();
+        }
+        todo &= ~group;
+    }
+    if (!live) {
+        if (empty) { nkey_t e[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) e[j] = PCC_EMPTY_KEY;
+            write_row<K>(e, k, out_idx + row * k, out_d2 + row * k, vec4); }
+        return;
+    }
+    // rings >= 2 per lane (ball-clipped), same as knn_fast_kernel
+    int R = 1;
+    float tau = (k == K) ? list.d[K - 1] : list.at(k - 1);
+    for (;;) {
+        const float cov = covered_d2(g, c, R);
+        if (cov == CUDART_INF_F || tau < cov) break;
+        const int Rin = R; R = next_ring(g, R, tau);
+        scan_clipped(g, c, Rin, R, to_cell_units(g, tau), [&](uint32_t pos, float4 p) {
+            const float d2 = dist2(x, y, z, p.x, p.y, p.z);
+            if (d2 <= list.d[K - 1]) { if (nlog < kCellLog) slog[nlog * 32] = pos; ++nlog; list.insert(d2); }
+        });
+        tau = (k == K) ? list.d[K - 1] : list.at(k - 1);
+    }
+    int m = 0;
+    if (nlog <= kCellLog) {
+        for (int i = 0; i < nlog; ++i) {
+            const uint32_t pos = slog[i * 32];
+            const float4 p = __ldg(g.pts + pos);
+            if (dist2(x, y, z, p.x, p.y, p.z) <= tau) { slog[m * 32] = pos; ++m; }
+        }
+    } else {
+        scan_clipped(g, c, -1, R, to_cell_units(g, tau), [&](uint32_t pos, float4 p) {
+            if (dist2(x, y, z, p.x, p.y, p.z) <= tau) { if (m < kCellLog) slog[m * 32] = pos; ++m; }
+        });
+    }
+    if (m > K) { fix.list[atomicAdd(fix.count, 1u)] = (uint32_t)t; return; }
+    nkey_t e[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        e[j] = PCC_EMPTY_KEY;
+        if (j < m) { const float4 p = __ldg(g.pts + slog[j * 32]); e[j] = make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w)); }
+    }
+    bitonic_sort_key<K>(e);
+    write_row<K>(e, k, out_idx + row * k, out_d2 + row * k, vec4);
+}
+
 // 32 < k <= PCC_MAX_K: per-thread max-heap in dynamic shared memory
 __global__ void knn_heap_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2) {
     extern __shared__ nkey_t smem_keys[];
@@ -406,6 +574,14 @@ static void launch_knn_reg(const Grid &g, const QueryView &v, int k, int32_t *oi
     PCC_LAUNCHED();
 }
 template <int K>
+static void launch_knn_cell(const Grid &g, const QueryView &v, int k, int32_t *oi, float *od, int vec4, FixList fix, cudaStream_t s) {
+    cudaMemsetAsync(fix.count, 0, sizeof(unsigned), s);
+    knn_cell_kernel<K><<<nblocks(v.nq, kCellWarps * 32), kCellWarps * 32, 0, s>>>(g, v, k, oi, od, vec4, fix);
+    PCC_LAUNCHED();
+    knn_fixup_kernel<K><<<148 * 4, 128, 0, s>>>(g, v, k, oi, od, vec4, fix);
+    PCC_LAUNCHED();
+}
+template <int K>
 static void launch_knn_fast(const Grid &g, const QueryView &v, int k, int32_t *oi, float *od, int vec4, FixList fix, cudaStream_t s) {
     cudaMemsetAsync(fix.count, 0, sizeof(unsigned), s);
     knn_fast_kernel<K><<<nblocks(v.nq, FastCfg<K>::threads), FastCfg<K>::threads, 0, s>>>(g, v, k, oi, od, vec4, fix);
@@ -454,6 +630,10 @@ int pcc_knn(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int k, 
     if (qs.nq > 0) {
         static const bool exact_only = getenv("PCC_EXACT_ONLY") != nullptr;     // debugging aid: force the ring-expansion path
         static const bool want_stats = getenv("PCC_STATS") != nullptr;
+        // warp-owns-a-cell TMA variant: opt-in (PCC_CELL_KERNEL=1).  Measured on B200 it is exact but 1.6-2.8x slower than the
+        // per-thread walk even at 80 queries per cell (profiles/r1/cell_kernel_probe.jsonl), so it is never chosen automatically.
+        const char *cell_env = getenv("PCC_CELL_KERNEL");
+        const bool use_cell = cell_env && atoi(cell_env) != 0;
         FixList fix{nullptr, nullptr, nullptr};
         if (k > 1 && k <= 32 && !exact_only) {
             PCC_TRY(idx->misc.reserve((size_t)v.nq * 4 + 128));
@@ -467,6 +647,9 @@ int pcc_knn(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int k, 
         else if (exact_only && k <= 8) launch_knn_reg<8>(g, v, k, oi, od, vec4, s);
         else if (exact_only && k <= 16) launch_knn_reg<16>(g, v, k, oi, od, vec4, s);
         else if (exact_only && k <= 32) launch_knn_reg<32>(g, v, k, oi, od, vec4, s);
+        else if (use_cell && k <= 8) launch_knn_cell<8>(g, v, k, oi, od, vec4, fix, s);
+        else if (use_cell && k <= 16) launch_knn_cell<16>(g, v, k, oi, od, vec4, fix, s);
+        else if (use_cell && k <= 32) launch_knn_cell<32>(g, v, k, oi, od, vec4, fix, s);
         else if (k <= 4) launch_knn_fast<4>(g, v, k, oi, od, vec4, fix, s);
         else if (k <= 8) launch_knn_fast<8>(g, v, k, oi, od, vec4, fix, s);
         else if (k <= 16) launch_knn_fast<16>(g, v, k, oi, od, vec4, fix, s);

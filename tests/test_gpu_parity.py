@@ -396,3 +396,22 @@ def test_voxel_grid_vs_oracle(GS):
     assert np.array_equal(dev.cpu().numpy().view(np.uint32), oracle.voxel_grid(rows, 0.025, rgb_offset_floats=4).view(np.uint32))
     xyz = synth.uniform(100000, 5, 2.0)                        # packed xyz rows, no colour
     assert np.array_equal(voxel_grid(xyz, 0.05).view(np.uint32), oracle.voxel_grid(xyz, 0.05).view(np.uint32))
+
+
+def test_tma_cell_kernel_variant_is_exact(GS, monkeypatch):
+    """The opt-in warp-owns-a-cell variant (cp.async.bulk-staged stencil tiles, PCC_CELL_KERNEL=1) returns the same rows."""
+    monkeypatch.setenv("PCC_CELL_KERNEL", "1")
+    ref = synth.room(150000, 1001)
+    qry = np.concatenate([synth.sweep_queries(ref, 400000, seed=3, sigma=0.01), ref[:1000], np.full((3, 3), np.nan, np.float32),
+                          np.random.default_rng(1).uniform(-2, 8, (500, 3)).astype(np.float32)])
+    tree = oracle.KdTree(ref)
+    for k, hint in ((16, 16), (5, 16), (32, 32), (16, 64)):          # hint 64: dense cells -> stencils larger than one 320-point tile
+        s = GS().setInputCloud(ref, k_hint=hint)
+        gi, gd, _ = s.nearestKSearch(qry, k)
+        oi, od, _ = tree.knn(qry, k)
+        assert_knn_equal(gi, gd, oi, od)
+    g = np.arange(12, dtype=np.float32) * 0.5                          # lattice: ties -> fix-up path from the cell kernel
+    lat = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    gi, gd, _ = GS().setInputCloud(lat).nearestKSearch(lat, 8)
+    oi, od, _ = oracle.brute_knn(lat, lat, 8)
+    assert_knn_equal(gi, gd, oi, od)
