@@ -70,11 +70,19 @@ struct pcc_index {
     bool timing = false;
     double last_ms = -1;
 
+    // host-buffer calls on large batches are pipelined over two slots (this index and a scratch-only shadow that borrows
+    // the grid): chunk i copies in / searches / copies out on stream i & 1, so PCIe traffic of one chunk overlaps the
+    // kernels of the other
+    pcc_index *shadow = nullptr;
+    const pcc_index *grid_owner = nullptr;
+    cudaStream_t pipe_stream[2] = {nullptr, nullptr};
+
     pcc::Grid grid() const {
+        const pcc_index *o = grid_owner ? grid_owner : this;
         pcc::Grid g;
-        g.pts = pts.as<float4>(); g.cell_start = cell_start.as<uint32_t>();
-        g.ox = gh.ox; g.oy = gh.oy; g.oz = gh.oz; g.inv_cell = gh.inv_cell; g.cell = gh.cell;
-        g.nx = gh.nx; g.ny = gh.ny; g.nz = gh.nz; g.n = (uint32_t)n_indexed;
+        g.pts = o->pts.as<float4>(); g.cell_start = o->cell_start.as<uint32_t>();
+        g.ox = o->gh.ox; g.oy = o->gh.oy; g.oz = o->gh.oz; g.inv_cell = o->gh.inv_cell; g.cell = o->gh.cell;
+        g.nx = o->gh.nx; g.ny = o->gh.ny; g.nz = o->gh.nz; g.n = (uint32_t)o->n_indexed;
         return g;
     }
 };

@@ -603,10 +603,10 @@ static int check_common(pcc_index *idx) {
 
 extern "C" {
 
-int pcc_knn(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int k, int32_t *out_idx, float *out_d2, int *k_eff, int mem, void *stream) {
-    PCC_TRY(check_common(idx));
-    if (k < 1 || k > PCC_MAX_K) return fail(PCC_ERR_INVALID, "k=%d outside 1..%d", k, PCC_MAX_K);
-    cudaStream_t s = (cudaStream_t)stream;
+}  // extern "C"
+
+// one batch on one stream; `sync` = wait for the host copies before returning (PCC_HOST only)
+static int knn_impl(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int k, int32_t *out_idx, float *out_d2, int *k_eff, int mem, cudaStream_t s, bool sync) {
     Queries qs;
     PCC_TRY(prepare_queries(idx, q, nq, stride_bytes, mem, s, &qs));
     if (k_eff) *k_eff = (int)std::min<int64_t>(k, idx->n_indexed);
@@ -673,9 +673,43 @@ int pcc_knn(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int k, 
     if (mem == PCC_HOST) {
         PCC_TRY(copy_out(out_idx, oi, cells * 4, mem, s));
         PCC_TRY(copy_out(out_d2, od, cells * 4, mem, s));
-        PCC_CUDA(cudaStreamSynchronize(s));
+        if (sync) PCC_CUDA(cudaStreamSynchronize(s));
     }
     return PCC_OK;
+}
+
+extern "C" {
+
+int pcc_knn(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int k, int32_t *out_idx, float *out_d2, int *k_eff, int mem, void *stream) {
+    PCC_TRY(check_common(idx));
+    if (k < 1 || k > PCC_MAX_K) return fail(PCC_ERR_INVALID, "k=%d outside 1..%d", k, PCC_MAX_K);
+    cudaStream_t s = (cudaStream_t)stream;
+    // Large host batches: two-slot pipeline, 1 Mi queries per chunk (16 MB in, k x 8 MB out), so the device->host copy of
+    // chunk i overlaps the search of chunk i+1 and the host->device copy of chunk i+2 (PCIe is full duplex).
+    static constexpr int64_t kChunk = 1 << 20;
+    if (mem == PCC_HOST && q && nq >= 2 * kChunk && !idx->timing && stride_bytes >= 12 && !(stride_bytes & 3)) {
+        if (!out_idx || !out_d2) return fail(PCC_ERR_INVALID, "output pointers are NULL");
+        if (!idx->shadow) {
+            idx->shadow = new pcc_index();
+            idx->shadow->device = idx->device;
+            idx->shadow->grid_owner = idx;
+            PCC_CUDA(cudaMallocHost(&idx->shadow->h_pinned, 4096));
+            for (int i = 0; i < 2; ++i) PCC_CUDA(cudaStreamCreateWithFlags(&idx->pipe_stream[i], cudaStreamNonBlocking));
+        }
+        pcc_index *sh = idx->shadow;
+        sh->built = true; sh->n_input = idx->n_input; sh->n_indexed = idx->n_indexed; sh->gh = idx->gh;
+        PCC_CUDA(cudaStreamSynchronize(s));                      // work queued on the caller's stream comes first
+        int rc = PCC_OK;
+        int64_t c0 = 0;
+        for (int i = 0; c0 < nq && rc == PCC_OK; ++i, c0 += kChunk) {
+            const int64_t n = std::min(kChunk, nq - c0);
+            rc = knn_impl((i & 1) ? sh : idx, (const uint8_t *)q + c0 * stride_bytes, n, stride_bytes, k, out_idx + c0 * k, out_d2 + c0 * k, k_eff, PCC_HOST, idx->pipe_stream[i & 1], false);
+        }
+        cudaStreamSynchronize(idx->pipe_stream[0]);
+        cudaStreamSynchronize(idx->pipe_stream[1]);
+        return rc;
+    }
+    return knn_impl(idx, q, nq, stride_bytes, k, out_idx, out_d2, k_eff, mem, s, true);
 }
 
 int pcc_knn_mean_dist(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int mean_k, float *out_mean, int mem, void *stream) {

@@ -415,3 +415,17 @@ def test_tma_cell_kernel_variant_is_exact(GS, monkeypatch):
     gi, gd, _ = GS().setInputCloud(lat).nearestKSearch(lat, 8)
     oi, od, _ = oracle.brute_knn(lat, lat, 8)
     assert_knn_equal(gi, gd, oi, od)
+
+
+def test_pipelined_host_path_large_batch(GS):
+    """Host-buffer batches >= 2 Mi queries go through the two-slot chunked pipeline; rows must equal the one-shot device path."""
+    import torch
+    ref = synth.room(300000, 1001, stride4=True)
+    qry = synth.sweep_queries(ref, 2_600_001, seed=4, sigma=0.01, stride4=True)
+    s = GS().setInputCloud(ref, k_hint=16)
+    hi, hd, keff = s.nearestKSearch(qry, 16)                                   # numpy -> PCC_HOST -> pipelined
+    di, dd, _ = s.nearestKSearch(torch.from_numpy(qry).cuda(), 16)             # one launch
+    assert keff == 16 and np.array_equal(hi, di.cpu().numpy()) and np.array_equal(bits(hd), bits(dd.cpu().numpy()))
+    sel = np.random.default_rng(2).choice(len(qry), 20000, replace=False)
+    oi, od, _ = oracle.KdTree(ref).knn(qry[sel], 16)
+    assert_knn_equal(hi[sel], hd[sel], oi, od)
