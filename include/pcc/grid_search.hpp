@@ -14,6 +14,7 @@
 //   pcc::EuclideanClusterExtraction  <- pcl::EuclideanClusterExtraction  (src/segmentation.cpp:125-131)
 //   pcc::IterativeClosestPoint       <- pcl::IterativeClosestPoint       (src/comparator.cpp:1089-1110)
 //   pcc::findPointNeighbours         <- RegionGrowing(RGB)::findPointNeighbours (src/segmentation.cpp:271,190)
+//   pcc::VoxelGrid                   <- pcl::VoxelGrid                   (src/segmentation.cpp:69-74,223-228)
 // There is no CPU fallback: a failing CUDA call throws pcc::Error.
 #ifndef PCC_GRID_SEARCH_HPP_
 #define PCC_GRID_SEARCH_HPP_
@@ -337,6 +338,34 @@ class IterativeClosestPoint {
   private:
     typename search::GridSearch<PointT>::PointCloudConstPtr source_, target_;
     int max_iter_ = 10, converged_ = 0, iterations_ = 0; double fitness_ = 0; float T_[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+};
+
+// pcl::VoxelGrid<PointT>: setLeafSize + filter (src/segmentation.cpp:69-74, 223-228).  One centroid per occupied voxel, ordered
+// by voxel index; for colour points pass the byte offset of the packed rgb word (16 for pcl::PointXYZRGB), else -1.
+template <typename PointT>
+class VoxelGrid {
+  public:
+    explicit VoxelGrid(int rgb_offset_bytes = -1, int device = 0) : rgb_off_(rgb_offset_bytes) { check(pcc_create(device, &ws_)); }
+    ~VoxelGrid() { pcc_destroy(ws_); }
+    VoxelGrid(const VoxelGrid &) = delete;
+    VoxelGrid &operator=(const VoxelGrid &) = delete;
+    void setInputCloud(const typename search::GridSearch<PointT>::PointCloudConstPtr &cloud) { input_ = cloud; }
+    void setLeafSize(float lx, float ly, float lz) { leaf_[0] = lx; leaf_[1] = ly; leaf_[2] = lz; }
+    void setMinimumPointsNumberPerVoxel(int n) { min_points_ = n; }
+    void filter(typename search::GridSearch<PointT>::PointCloud &output) {
+        const size_t n = input_->points.size();
+        std::vector<PointT> out(n);
+        int64_t n_out = 0;
+        if (n) check(pcc_voxel_grid(ws_, input_->points.data(), (int64_t)n, (int)sizeof(PointT), rgb_off_, leaf_, min_points_, out.data(), &n_out, PCC_HOST, nullptr));
+        out.resize((size_t)n_out);
+        output.points.swap(out);
+        output.width = (std::uint32_t)output.points.size(); output.height = 1; output.is_dense = true;
+    }
+  private:
+    pcc_index *ws_ = nullptr;
+    typename search::GridSearch<PointT>::PointCloudConstPtr input_;
+    float leaf_[3] = {0.01f, 0.01f, 0.01f};
+    int rgb_off_ = -1, min_points_ = 0;
 };
 
 // RegionGrowing(RGB)::findPointNeighbours: the dense N x k neighbour (and distance) table the sequential grow phase consumes.

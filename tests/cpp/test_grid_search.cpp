@@ -119,9 +119,14 @@ int main() {
     const float *T = icp.getFinalTransformation();
     REQUIRE(std::fabs(T[3] + 0.01f) < 2e-3f && std::fabs(T[7] - 0.005f) < 2e-3f && icp.getFitnessScore() < 1e-5);
 
+    pcc::VoxelGrid<P> vg(16); vg.setInputCloud(cloud); vg.setLeafSize(0.025f, 0.025f, 0.025f);
+    Cloud down; vg.filter(down);
+    REQUIRE(down.size() > 1000 && down.size() < cloud->size());
+    for (size_t i = 0; i < down.size(); ++i) REQUIRE(finite(down[i]) && down[i]._pad == 1.0f);
+
     std::vector<int> tab; std::vector<float> tabd;
     REQUIRE(pcc::findPointNeighbours(*tree, 100, tab, tabd) == 100 && tab.size() == cloud->size() * 100);
 
-    std::printf("PASS grid_search host mirror: kNN/radius/indices/normals/SOR/ECE/ICP/neighbour-table (%lld kernel launches)\n", (long long)pcc_launch_count());
+    std::printf("PASS grid_search host mirror: kNN/radius/indices/normals/SOR/ECE/ICP/VoxelGrid/neighbour-table (%lld kernel launches)\n", (long long)pcc_launch_count());
     return 0;
 }
