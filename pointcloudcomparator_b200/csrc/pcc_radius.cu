@@ -64,6 +64,62 @@ __global__ void radius_capped_kernel(Grid g, QueryView v, float r2, int R0, int 
     nkey_t *o = keys + offsets[row];
     for (int j = 0; j < list.cnt; ++j) o[j] = list.at(j);
 }
+// ---- per-row sort of the CSR rows by the packed (d2, idx) key ----
+// cub::DeviceSegmentedSort took 475 ms for 722 M keys in 5 M rows of ~144 (its large-segment path, one block per row);
+// radius rows are short, so one WARP sorts one row: <= 32 keys in registers with shuffles, <= 1024 keys with a bitonic
+// network in the warp's shared-memory slice.  Longer rows are listed and sorted by the library afterwards.
+static constexpr int kRowSortWarps = 4, kRowSortCap = 1024;
+__global__ void __launch_bounds__(kRowSortWarps * 32) sort_rows_kernel(const int64_t *__restrict__ offsets, int64_t rows, nkey_t *__restrict__ keys,
+                                                                       uint32_t *__restrict__ big_rows, unsigned *__restrict__ n_big) {
+    __shared__ nkey_t sm_all[kRowSortWarps][kRowSortCap];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kRowSortWarps + warp;
+    if (row >= rows) return;
+    const int64_t b = offsets[row];
+    const int64_t n64 = offsets[row + 1] - b;
+    if (n64 <= 1) return;
+    if (n64 > kRowSortCap) { if (lane == 0) big_rows[atomicAdd(n_big, 1u)] = (uint32_t)row; return; }
+    const int n = (int)n64;
+    nkey_t *k = keys + b;
+    if (n <= 32) {                                    // one key per lane, compare-exchange through shuffles
+        nkey_t v = lane < n ? k[lane] : PCC_EMPTY_KEY;
+#pragma unroll
+        for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                const nkey_t o = __shfl_xor_sync(0xffffffffu, v, j);
+                const bool up = (lane & kk) == 0, lower = (lane & j) == 0;
+                const nkey_t mn = v < o ? v : o, mx = v < o ? o : v;
+                v = (lower == up) ? mn : mx;
+            }
+        }
+        if (lane < n) k[lane] = v;
+        return;
+    }
+    nkey_t *sm = sm_all[warp];
+    int P = 64; while (P < n) P <<= 1;
+    for (int i = lane; i < P; i += 32) sm[i] = i < n ? k[i] : PCC_EMPTY_KEY;
+    __syncwarp();
+    for (int kk = 2; kk <= P; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (P >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const nkey_t a = sm[i], c = sm[i + j];
+                const bool up = (i & kk) == 0;
+                if ((c < a) == up) { sm[i] = c; sm[i + j] = a; }
+            }
+            __syncwarp();
+        }
+    }
+    for (int i = lane; i < n; i += 32) k[i] = sm[i];
+}
+__global__ void big_row_bounds_kernel(const int64_t *__restrict__ offsets, const uint32_t *__restrict__ big_rows, unsigned n_big, int64_t *__restrict__ begin, int64_t *__restrict__ end) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_big) { begin[i] = offsets[big_rows[i]]; end[i] = offsets[big_rows[i] + 1]; }
+}
+__global__ void big_row_copy_kernel(const int64_t *__restrict__ begin, const int64_t *__restrict__ end, const nkey_t *__restrict__ src, nkey_t *__restrict__ dst) {
+    for (int64_t i = begin[blockIdx.x] + threadIdx.x; i < end[blockIdx.x]; i += blockDim.x) dst[i] = src[i];
+}
 __global__ void unpack_kernel(const nkey_t *__restrict__ keys, int64_t n, int32_t *__restrict__ idx, float *__restrict__ d2) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -226,15 +282,31 @@ static int radius_rows(pcc_index *idx, const Queries &qs, double radius, unsigne
     PCC_LAUNCHED();
     PCC_CUDA(cudaGetLastError());
     if (sorted) {
-        if (total >= (1ll << 31)) return fail(PCC_ERR_INVALID, "radius result of %lld neighbours exceeds the segmented-sort limit", (long long)total);
-        PCC_TRY(idx->keys64b.reserve((size_t)total * sizeof(nkey_t)));
-        cub::DoubleBuffer<nkey_t> db(keys, idx->keys64b.as<nkey_t>());
-        size_t tmp = 0;
-        cub::DeviceSegmentedSort::SortKeys(nullptr, tmp, db, (int)total, (int)qs.rows, d_offsets, d_offsets + 1, s);
-        PCC_TRY(idx->cub_tmp.reserve(tmp));
-        PCC_CUDA(cub::DeviceSegmentedSort::SortKeys(idx->cub_tmp.p, tmp, db, (int)total, (int)qs.rows, d_offsets, d_offsets + 1, s));
-        g_launches += 3;
-        *keys_out = db.Current();
+        PCC_TRY(idx->misc.reserve((size_t)qs.rows * 4 + 64));
+        unsigned *n_big = idx->misc.as<unsigned>();
+        uint32_t *big_rows = idx->misc.as<uint32_t>() + 16;
+        PCC_CUDA(cudaMemsetAsync(n_big, 0, 4, s));
+        sort_rows_kernel<<<nblocks(qs.rows, kRowSortWarps), kRowSortWarps * 32, 0, s>>>(d_offsets, qs.rows, keys, big_rows, n_big);
+        PCC_LAUNCHED();
+        PCC_CUDA(cudaGetLastError());
+        unsigned *h = (unsigned *)idx->h_pinned;
+        PCC_CUDA(cudaMemcpyAsync(h, n_big, 4, cudaMemcpyDeviceToHost, s));
+        PCC_CUDA(cudaStreamSynchronize(s));
+        const unsigned nb = h[0];
+        if (nb > 0) {       // rows longer than 1024 neighbours: library segmented sort over just those rows
+            if (total >= (1ll << 31)) return fail(PCC_ERR_INVALID, "radius result of %lld neighbours exceeds the segmented-sort limit", (long long)total);
+            PCC_TRY(idx->keys64b.reserve((size_t)total * sizeof(nkey_t)));
+            PCC_TRY(idx->parent.reserve((size_t)nb * 16));
+            int64_t *bb = idx->parent.as<int64_t>(), *be = bb + nb;
+            big_row_bounds_kernel<<<nblocks(nb, 256), 256, 0, s>>>(d_offsets, big_rows, nb, bb, be); PCC_LAUNCHED();
+            size_t tmp = 0;
+            cub::DeviceSegmentedSort::SortKeys(nullptr, tmp, keys, idx->keys64b.as<nkey_t>(), (int)total, (int)nb, bb, be, s);
+            PCC_TRY(idx->cub_tmp.reserve(tmp));
+            PCC_CUDA(cub::DeviceSegmentedSort::SortKeys(idx->cub_tmp.p, tmp, keys, idx->keys64b.as<nkey_t>(), (int)total, (int)nb, bb, be, s));
+            g_launches += 3;
+            big_row_copy_kernel<<<nb, 256, 0, s>>>(bb, be, idx->keys64b.as<nkey_t>(), keys); PCC_LAUNCHED();
+            PCC_CUDA(cudaGetLastError());
+        }
     }
     return PCC_OK;
 }

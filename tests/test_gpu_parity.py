@@ -429,3 +429,18 @@ def test_pipelined_host_path_large_batch(GS):
     sel = np.random.default_rng(2).choice(len(qry), 20000, replace=False)
     oi, od, _ = oracle.KdTree(ref).knn(qry[sel], 16)
     assert_knn_equal(hi[sel], hd[sel], oi, od)
+
+
+def test_radius_rows_of_every_length(GS):
+    """Row sort tiers: <= 32 keys (shuffles), <= 1024 (shared-memory bitonic), longer (library fallback) -- all (d2, idx)-sorted."""
+    rng = np.random.default_rng(9)
+    ref = np.concatenate([rng.normal(0, 0.02, (6000, 3)), rng.random((20000, 3)) * 2.0 + 1.0]).astype(np.float32)   # a dense blob + sparse volume
+    qry = np.concatenate([ref[:300], ref[6000:9000], rng.random((200, 3)).astype(np.float32) * 3])
+    tree = oracle.KdTree(ref)
+    for r in (0.04, 0.12, 0.3):
+        s = GS().setInputCloud(ref, cell_hint=r)
+        off, idx, d2 = s.radiusSearch(qry, r)
+        ooff, oidx, od2 = tree.radius(qry, r)
+        lens = np.diff(ooff)
+        assert np.array_equal(off, ooff) and np.array_equal(idx, oidx) and np.array_equal(bits(d2), bits(od2)), (r, lens.max())
+    assert lens.max() > 1024 and (lens <= 32).any() and ((lens > 32) & (lens <= 1024)).any()
