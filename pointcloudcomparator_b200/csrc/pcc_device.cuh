@@ -164,6 +164,27 @@ __device__ __forceinline__ void scan_clipped(const Grid &g, const QueryCell &c, 
     }
 }
 
+// Same walk, but the clipping ball is re-read before every row (`tau_now()` returns the current squared radius in cell
+// units).  It pays when a pass is large: a far query (ICP's first iterations, outliers) doubles its block until it sees
+// the first point, and from that row on the rest of the SAME pass is clipped to the ball of the best distance so far
+// instead of scanning the whole block.  (The bounds of row i+1 are fetched before row i is walked, so a row is clipped
+// with the radius known one row earlier -- conservative, never wrong.)
+template <class T, class F>
+__device__ __forceinline__ void scan_progressive(const Grid &g, const QueryCell &c, int Rin, int Rout, T &&tau_now, F &&f) {
+    const int n1 = 2 * Rout + 1;
+    int az = 0, ay = 0;
+    RowRuns nxt = row_runs(g, c, Rin, Rout, tau_now(), 0, 0);
+    for (;;) {
+        const RowRuns cur = nxt;
+        if (++ay == n1) { ay = 0; ++az; }
+        const bool more = az < n1;
+        if (more) nxt = row_runs(g, c, Rin, Rout, tau_now(), az, ay);
+        walk_run(g, cur.j1, cur.e1, f);
+        walk_run(g, cur.j2, cur.e2, f);
+        if (!more) break;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // top-k containers.  Entries are 64-bit keys (fp32 d2 bits << 32 | payload): d2 >= +0 so the
 // unsigned order of the bits is the numeric order, and one 64-bit compare gives the canonical

@@ -36,13 +36,12 @@ template <class List>
 __device__ __forceinline__ void knn_search(const Grid &g, float x, float y, float z, int k, List &list) {
     const QueryCell c = locate(g, x, y, z);
     int Rin = -1, R = 1;
-    float clip = CUDART_INF_F;      // ball of the current k-th distance (cell units): rings >= 2 only touch cells inside it
     for (;;) {
-        scan_clipped(g, c, Rin, R, clip, [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
+        scan_progressive(g, c, Rin, R, [&]() { return to_cell_units(g, key_d2(list.at(k - 1))); },
+                         [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
         const float cov = covered_d2(g, c, R);
         if (cov == CUDART_INF_F) break;
         const nkey_t kth = list.at(k - 1);
-        clip = to_cell_units(g, key_d2(kth));
         if (kth != PCC_EMPTY_KEY && key_d2(kth) < cov) break;
         Rin = R; R = next_ring(g, R, key_d2(kth));
     }
@@ -110,7 +109,7 @@ __device__ __forceinline__ float kth_distance(const Grid &g, const QueryCell &c,
     int Rin = -1, R = 1;
     float kth = CUDART_INF_F;
     for (;;) {
-        scan_clipped(g, c, Rin, R, to_cell_units(g, kth), [&](uint32_t pos, float4 p) {
+        scan_progressive(g, c, Rin, R, [&]() { return to_cell_units(g, (k == K) ? list.d[K - 1] : list.at(k - 1)); }, [&](uint32_t pos, float4 p) {
             const float d2 = dist2(x, y, z, p.x, p.y, p.z);
             if (d2 <= list.d[K - 1]) {            // "<=": a candidate tied with the final k-th distance must be in the log too
                 if (nlog < FastCfg<K>::log_slots) slog[nlog * FastCfg<K>::threads] = pos;
@@ -312,7 +311,7 @@ __global__ void __launch_bounds__(kCellWarps * 32, 5) knn_cell_kernel(Grid g, Qu
         const float cov = covered_d2(g, c, R);
         if (cov == CUDART_INF_F || tau < cov) break;
         const int Rin = R; R = next_ring(g, R, tau);
-        scan_clipped(g, c, Rin, R, to_cell_units(g, tau), [&](uint32_t pos, float4 p) {
+        scan_progressive(g, c, Rin, R, [&]() { return to_cell_units(g, (k == K) ? list.d[K - 1] : list.at(k - 1)); }, [&](uint32_t pos, float4 p) {
             const float d2 = dist2(x, y, z, p.x, p.y, p.z);
             if (d2 <= list.d[K - 1]) { if (nlog < kCellLog) slog[nlog * 32] = pos; ++nlog; list.insert(d2); }
         });
@@ -352,13 +351,12 @@ __global__ void knn_heap_kernel(Grid g, QueryView v, int k, int32_t *__restrict_
     if (live) {
         const QueryCell c = locate(g, x, y, z);
         int Rin = -1, R = 1;
-        float clip = CUDART_INF_F;
         for (;;) {
-            scan_clipped(g, c, Rin, R, clip, [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
+            scan_progressive(g, c, Rin, R, [&]() { return list.full() ? to_cell_units(g, key_d2(list.worst())) : CUDART_INF_F; },
+                             [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
             const float cov = covered_d2(g, c, R);
             if (cov == CUDART_INF_F) break;
             if (list.full() && key_d2(list.worst()) < cov) break;
-            if (list.full()) clip = to_cell_units(g, key_d2(list.worst()));
             Rin = R; R = next_ring(g, R, list.full() ? key_d2(list.worst()) : CUDART_INF_F);
         }
     }
@@ -378,13 +376,11 @@ __global__ void __launch_bounds__(128, (K <= 17 ? 8 : (K <= 33 ? 6 : 4))) mean_d
     RegDist<K> list; list.init();
     const QueryCell c = locate(g, x, y, z);
     int Rin = -1, R = 1;
-    float clip = CUDART_INF_F;
     for (;;) {
-        scan_clipped(g, c, Rin, R, clip, [&](uint32_t, float4 p) { list.offer(dist2(x, y, z, p.x, p.y, p.z)); });
+        scan_progressive(g, c, Rin, R, [&]() { return to_cell_units(g, EXACT ? list.d[K - 1] : list.at(mean_k)); }, [&](uint32_t, float4 p) { list.offer(dist2(x, y, z, p.x, p.y, p.z)); });
         const float cov = covered_d2(g, c, R);
         if (cov == CUDART_INF_F) break;
         const float kth = EXACT ? list.d[K - 1] : list.at(mean_k);
-        clip = to_cell_units(g, kth);
         if (kth < cov) break;
         Rin = R; R = next_ring(g, R, kth);
     }
@@ -407,13 +403,12 @@ __global__ void mean_dist_heap_kernel(Grid g, QueryView v, int mean_k, float *__
     HeapList list; list.init(smem_keys + threadIdx.x, blockDim.x, mean_k + 1);
     const QueryCell c = locate(g, x, y, z);
     int Rin = -1, R = 1;
-    float clip = CUDART_INF_F;
     for (;;) {
-        scan_clipped(g, c, Rin, R, clip, [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
+        scan_progressive(g, c, Rin, R, [&]() { return list.full() ? to_cell_units(g, key_d2(list.worst())) : CUDART_INF_F; },
+                             [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
         const float cov = covered_d2(g, c, R);
         if (cov == CUDART_INF_F) break;
         if (list.full() && key_d2(list.worst()) < cov) break;
-        if (list.full()) clip = to_cell_units(g, key_d2(list.worst()));
         Rin = R; R = next_ring(g, R, list.full() ? key_d2(list.worst()) : CUDART_INF_F);
     }
     list.finish();
@@ -445,13 +440,12 @@ __global__ void normals_knn_heap_kernel(Grid g, QueryView v, int k, const uint32
     HeapList list; list.init(smem_keys + threadIdx.x, blockDim.x, k);
     const QueryCell c = locate(g, x, y, z);
     int Rin = -1, R = 1;
-    float clip = CUDART_INF_F;
     for (;;) {
-        scan_clipped(g, c, Rin, R, clip, [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
+        scan_progressive(g, c, Rin, R, [&]() { return list.full() ? to_cell_units(g, key_d2(list.worst())) : CUDART_INF_F; },
+                             [&](uint32_t, float4 p) { list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); });
         const float cov = covered_d2(g, c, R);
         if (cov == CUDART_INF_F) break;
         if (list.full() && key_d2(list.worst()) < cov) break;
-        if (list.full()) clip = to_cell_units(g, key_d2(list.worst()));
         Rin = R; R = next_ring(g, R, list.full() ? key_d2(list.worst()) : CUDART_INF_F);
     }
     list.finish();
@@ -488,7 +482,7 @@ __global__ void __launch_bounds__(kIcpThreads) icp_step_kernel(Grid g, float4 *_
                 const QueryCell c = locate(g, p.x, p.y, p.z);
                 int Rin = -1, R = 1;
                 for (;;) {
-                    scan_clipped(g, c, Rin, R, to_cell_units(g, key_d2(best)), [&](uint32_t pos, float4 r) {
+                    scan_progressive(g, c, Rin, R, [&]() { return to_cell_units(g, key_d2(best)); }, [&](uint32_t pos, float4 r) {
                         const nkey_t k = make_key(dist2(p.x, p.y, p.z, r.x, r.y, r.z), __float_as_uint(r.w));
                         if (k < best) { best = k; bpos = pos; }
                     });
