@@ -44,7 +44,7 @@ if "c3" in which:   # -e Euclidean clusters on the 5M scene
 if "c4" in which:   # -i ICP 10M vs 10M
     src, tgt, T = synth.icp_pair(10_000_000, 4001, stride4=True)
     ds, dt = torch.from_numpy(src).cuda(), torch.from_numpy(tgt).cuda()
-    s = GridSearch(0); tb, _ = timed(lambda: s.setInputCloud(dt, k_hint=1), 1)
+    s = GridSearch(0); tb, _ = timed(lambda: s.setInputCloud(dt, k_hint=32), 1)     # coarse cells: the first iterations search from far away
     t1, r1 = timed(lambda: s.icpStep(ds.clone(), None), 2)
     ta, r = timed(lambda: s.icpAlign(ds, 20), 1)
     emit(config="C4 icp-10M", build_ms=tb, one_pass_ms=t1, align_ms=ta, iterations=r["iterations"], converged=r["converged"], fitness=r["fitness"],
