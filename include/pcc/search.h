@@ -141,6 +141,13 @@ int pcc_first_within(pcc_index *idx, const void *q, int64_t nq, int stride_bytes
 int pcc_voxel_grid(pcc_index *idx, const void *pts, int64_t n, int stride_bytes, int rgb_offset_bytes, const float leaf[3],
                    int min_points_per_voxel, void *out, int64_t *n_out, int mem, void *stream);
 
+/* matchRIFTFeaturesKnn (src/comparator.cpp:560-588): KdTreeFLANN<Histogram<32>> over `ref`, nearestKSearch(k = 1) for every row
+ * of `qry` [up].  Exact brute force in descriptor space: d2 accumulated sequentially over the `dim` floats of a row (fp32, no
+ * FMA), ties to the lowest index, non-finite reference rows skipped, non-finite queries get (-1, +inf).  The caller applies
+ * the reference's acceptance test (d2 < 0.05f).  dim = 32 (RIFT32) is instantiated; rows are stride_floats floats apart. */
+int pcc_descriptor_nn(pcc_index *workspace, const float *ref, int64_t n_ref, const float *qry, int64_t n_qry, int dim, int stride_floats,
+                      int32_t *out_idx, float *out_d2, int mem, void *stream);
+
 /* Multi-GPU plumbing (query sharding with a replicated grid): the built index is four flat device
  * arrays that a host layer can broadcast with NCCL and adopt on the other ranks.
  * meta[16] (host doubles): n_indexed, n_input, nx, ny, nz, origin xyz, cell, inv_cell, mean occupancy, n_cells.

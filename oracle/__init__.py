@@ -55,6 +55,7 @@ def lib():
         L.orc_first_within.argtypes = [f32p, i64, i32, f32p, i64, i32, dbl, i32p]
         L.orc_voxel_grid.restype = i64
         L.orc_voxel_grid.argtypes = [f32p, i64, i32, i32, f32p, i32, f32p]
+        L.orc_descriptor_nn.argtypes = [f32p, i64, f32p, i64, i32, i32p, f32p]
         L.orc_num_threads.restype = i32
         _lib = L
     return _lib
@@ -226,3 +227,11 @@ def voxel_grid(rows, leaf, rgb_offset_floats: int = -1, min_points: int = 0):
     if n < 0:
         raise ValueError("leaf size is too small for the input dataset")
     return out[:n]
+
+
+def descriptor_nn(ref, qry):
+    """matchRIFTFeaturesKnn's inner search: nearest reference descriptor of every query descriptor (index or -1, d2)."""
+    ref, qry = np.ascontiguousarray(ref, np.float32), np.ascontiguousarray(qry, np.float32)
+    idx, d2 = np.empty(qry.shape[0], np.int32), np.empty(qry.shape[0], np.float32)
+    lib().orc_descriptor_nn(_p(ref, C.c_float), ref.shape[0], _p(qry, C.c_float), qry.shape[0], ref.shape[1], _p(idx, C.c_int32), _p(d2, C.c_float))
+    return idx, d2

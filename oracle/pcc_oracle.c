@@ -741,6 +741,23 @@ ORC_API int64_t orc_voxel_grid(const float *pts, int64_t n, int stride_f, int rg
     return total;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* matchRIFTFeaturesKnn (src/comparator.cpp:560-588): 1-NN in descriptor space, FLANN L2_Simple over `dim` floats.
+ * Brute force restatement (the reference uses a kd-tree; exact search, same result wherever d2 is unique). */
+ORC_API void orc_descriptor_nn(const float *ref, int64_t n_ref, const float *qry, int64_t n_qry, int dim, int32_t *out_idx, float *out_d2) {
+    for (int64_t t = 0; t < n_qry; ++t) {
+        const float *q = qry + t * dim; int qok = 1;
+        for (int i = 0; i < dim; ++i) qok &= isfinite(q[i]) != 0;
+        float best = INFINITY; int32_t bi = -1;
+        if (qok) for (int64_t r = 0; r < n_ref; ++r) {
+            const float *p = ref + r * dim; int ok = 1; float d2 = 0.f;
+            for (int i = 0; i < dim; ++i) { ok &= isfinite(p[i]) != 0; float diff = q[i] - p[i]; d2 += diff * diff; }
+            if (ok && d2 < best) { best = d2; bi = (int32_t)r; }
+        }
+        out_idx[t] = bi; out_d2[t] = best;
+    }
+}
+
 ORC_API int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -444,3 +444,22 @@ def test_radius_rows_of_every_length(GS):
         lens = np.diff(ooff)
         assert np.array_equal(off, ooff) and np.array_equal(idx, oidx) and np.array_equal(bits(d2), bits(od2)), (r, lens.max())
     assert lens.max() > 1024 and (lens <= 32).any() and ((lens > 32) & (lens <= 1024)).any()
+
+
+def test_descriptor_nn_vs_oracle(GS):
+    """RIFT32 1-NN (src/comparator.cpp:560-588), bit-exact vs the oracle incl. the reference's vector shape."""
+    import torch
+    from pointcloudcomparator_b200.search import descriptor_nn, match_rift_features_knn
+    rng = np.random.default_rng(5)
+    for n1, n2 in ((1, 3), (63, 200), (700, 400), (5000, 3000)):
+        ref = rng.random((n1, 32), dtype=np.float32) * 0.3
+        qry = (ref[rng.integers(0, n1, n2)] + rng.normal(0, 0.03, (n2, 32))).astype(np.float32)
+        if n1 > 10:
+            ref[3, 9] = np.nan; qry[1, 31] = np.inf; ref[7] = ref[2]           # skipped row, empty query, exact duplicate (tie -> lower index)
+        gi, gd = descriptor_nn(ref, qry)
+        oi, od = oracle.descriptor_nn(ref, qry)
+        assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od))
+        di, dd = descriptor_nn(torch.from_numpy(ref).cuda(), torch.from_numpy(qry).cuda())
+        assert np.array_equal(di.cpu().numpy(), oi) and np.array_equal(bits(dd.cpu().numpy()), bits(od))
+        corr = match_rift_features_knn(ref, qry)
+        assert corr == [0] + oi[(oi >= 0) & (od < np.float32(0.05))].tolist()

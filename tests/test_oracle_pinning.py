@@ -187,3 +187,19 @@ def test_voxel_grid_known_answers():
     assert o.shape[0] == len(np.unique(ijk, axis=0))
     vox = np.floor(o[:, :3] * np.float32(1 / np.float32(0.025)) + 1e-4).astype(np.int64)
     assert len(np.unique(vox, axis=0)) >= 0.999 * o.shape[0]      # every centroid stays inside its own voxel (up to fp32 rounding on faces)
+
+
+def test_descriptor_nn_matches_opencv_flann_32d():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    ref = rng.random((700, 32), dtype=np.float32) * 0.3
+    qry = (ref[rng.integers(0, 700, 400)] + rng.normal(0, 0.02, (400, 32))).astype(np.float32)
+    fl = cv2.flann_Index(ref, dict(algorithm=4, leaf_max_size=15))          # same index family KdTreeFLANN<Histogram<32>> builds
+    ci, cd = fl.knnSearch(qry, 1, params=dict(checks=-1, eps=0.0, sorted=True))
+    oi, od = oracle.descriptor_nn(ref, qry)
+    # OpenCV's FLANN uses the 4-way unrolled cvflann::L2 functor (sums four squared differences per step); PCL's KdTreeFLANN
+    # uses L2_Simple (one dimension at a time), which the oracle restates.  Same neighbours, distances equal to a few ulp.
+    assert np.array_equal(ci[:, 0], oi) and np.allclose(cd[:, 0], od, rtol=1e-6, atol=0)
+    ref[5, 7] = np.nan; qry[3, 0] = np.inf
+    oi, od = oracle.descriptor_nn(ref, qry)
+    assert (oi != 5).all() and oi[3] == -1 and np.isinf(od[3])
