@@ -15,6 +15,7 @@
 //   pcc::IterativeClosestPoint       <- pcl::IterativeClosestPoint       (src/comparator.cpp:1089-1110)
 //   pcc::findPointNeighbours         <- RegionGrowing(RGB)::findPointNeighbours (src/segmentation.cpp:271,190)
 //   pcc::VoxelGrid                   <- pcl::VoxelGrid                   (src/segmentation.cpp:69-74,223-228)
+//   pcc::RegionGrowing               <- pcl::RegionGrowing               (src/segmentation.cpp:249-271)
 // There is no CPU fallback: a failing CUDA call throws pcc::Error.
 #ifndef PCC_GRID_SEARCH_HPP_
 #define PCC_GRID_SEARCH_HPP_
@@ -373,6 +374,48 @@ template <typename PointT>
 inline int findPointNeighbours(search::GridSearch<PointT> &tree, int k, std::vector<int> &neighbours, std::vector<float> &sqr_distances) {
     return tree.nearestKSearchTable(nullptr, 0, k, neighbours, sqr_distances);
 }
+
+// pcl::RegionGrowing<PointT, Normal>::extract: the N x k table comes from one batched GPU query, the order-dependent grow
+// phase runs on the host over it (pcc_region_growing).  Clusters come out in creation order, members ascending, as PCL's
+// assembleRegions leaves them.
+template <typename PointT>
+class RegionGrowing {
+  public:
+    void setSearchMethod(const typename search::GridSearch<PointT>::Ptr &tree) { tree_ = tree; }
+    void setInputCloud(const typename search::GridSearch<PointT>::PointCloudConstPtr &cloud) { input_ = cloud; }
+    void setInputNormals(const std::vector<Normal> *normals) { normals_ = normals; }
+    void setNumberOfNeighbours(unsigned int k) { k_ = (int)k; }
+    void setMinClusterSize(int n) { min_size_ = n; }
+    void setMaxClusterSize(int n) { max_size_ = n; }
+    void setSmoothnessThreshold(float theta) { theta_ = theta; }
+    void setCurvatureThreshold(float c) { curvature_ = c; }
+    void extract(std::vector<PointIndices> &clusters) {
+        clusters.clear();
+        if (!input_ || !normals_ || normals_->size() != input_->points.size()) throw Error("RegionGrowing: cloud and normals must be set and of equal size");
+        const size_t n = input_->points.size();
+        if (n == 0) return;
+        if (!tree_) tree_.reset(new search::GridSearch<PointT>());
+        tree_->setKHint(k_);
+        if (tree_->getInputCloud() != input_) tree_->setInputCloud(input_);
+        std::vector<int> nbrs; std::vector<float> d2;
+        findPointNeighbours(*tree_, k_, nbrs, d2);
+        std::vector<float> flat(n * 4);
+        for (size_t i = 0; i < n; ++i) { const Normal &m = (*normals_)[i]; flat[4 * i] = m.normal_x; flat[4 * i + 1] = m.normal_y; flat[4 * i + 2] = m.normal_z; flat[4 * i + 3] = m.curvature; }
+        labels_.assign(n, -1);
+        int64_t nc = 0;
+        check(pcc_region_growing(nbrs.data(), (int64_t)n, k_, flat.data(), theta_, curvature_, min_size_, max_size_, labels_.data(), &nc));
+        clusters.resize((size_t)nc);
+        for (size_t i = 0; i < n; ++i) if (labels_[i] >= 0) clusters[(size_t)labels_[i]].indices.push_back((int)i);
+    }
+    const std::vector<int32_t> &labels() const { return labels_; }
+  private:
+    typename search::GridSearch<PointT>::Ptr tree_;
+    typename search::GridSearch<PointT>::PointCloudConstPtr input_;
+    const std::vector<Normal> *normals_ = nullptr;
+    std::vector<int32_t> labels_;
+    int k_ = 30; int64_t min_size_ = 1, max_size_ = std::numeric_limits<int>::max();
+    float theta_ = 30.0f / 180.0f * 3.14159265358979f, curvature_ = 0.05f;
+};
 
 }  // namespace pcc
 #endif  // PCC_GRID_SEARCH_HPP_

@@ -141,6 +141,13 @@ int pcc_first_within(pcc_index *idx, const void *q, int64_t nq, int stride_bytes
 int pcc_voxel_grid(pcc_index *idx, const void *pts, int64_t n, int stride_bytes, int rgb_offset_bytes, const float leaf[3],
                    int min_points_per_voxel, void *out, int64_t *n_out, int mem, void *stream);
 
+/* RegionGrowing::extract minus findPointNeighbours (src/segmentation.cpp:249-271) [up]: the sequential smooth-region grow over
+ * the N x k neighbour table built by pcc_knn(q == NULL) and the normals of pcc_normals_knn (rows nx, ny, nz, curvature).
+ * HOST pointers only (the algorithm is order-dependent and runs on the host).  labels[i] = cluster number in creation
+ * order among the clusters with min_size <= size <= max_size, or -1. */
+int pcc_region_growing(const int32_t *neighbours, int64_t n, int k, const float *normals4, float smoothness_rad, float curvature_threshold,
+                       int64_t min_size, int64_t max_size, int32_t *labels, int64_t *n_clusters);
+
 /* matchRIFTFeaturesKnn (src/comparator.cpp:560-588): KdTreeFLANN<Histogram<32>> over `ref`, nearestKSearch(k = 1) for every row
  * of `qry` [up].  Exact brute force in descriptor space: d2 accumulated sequentially over the `dim` floats of a row (fp32, no
  * FMA), ties to the lowest index, non-finite reference rows skipped, non-finite queries get (-1, +inf).  The caller applies

