@@ -12,6 +12,9 @@
 #include <cmath>
 #include <cstring>
 
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+
 #include "pcc_internal.h"
 #include "pcc_fastknn.cuh"
 
@@ -75,7 +78,18 @@ __global__ void __launch_bounds__(128) knn_reg_kernel(Grid g, QueryView v, int k
     knn_reg_body<K>(g, v, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, k, out_idx, out_d2, vec4);
 }
 // queries the fast path could not prove exact (listed by knn_fast_kernel)
-struct FixList { uint32_t *list; unsigned *count; unsigned long long *stats; };   // stats: optional debug counters (PCC_STATS=1)
+// `ring_flag[t]` = 1 for the queries whose 3x3x3 block did not prove the k-th distance; a stream compaction turns the flags
+// into `ring_list` / `ring_count` IN PROCESSING ORDER (neighbouring lanes stay neighbours in space) for knn_rings_kernel.
+struct FixList { uint32_t *list; unsigned *count; unsigned long long *stats; uint32_t *ring_list; unsigned *ring_count; uint8_t *ring_flag; unsigned *ring_cursor; };   // stats: optional debug counters (PCC_STATS=1)
+// append `value` to a device list, one atomic per warp
+__device__ __forceinline__ void push_list(uint32_t *list, unsigned *count, uint32_t value) {
+    const unsigned mask = __activemask();
+    const int leader = __ffs(mask) - 1, lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(count, (unsigned)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    list[base + __popc(mask & ((1u << lane) - 1))] = value;
+}
 template <int K>
 __global__ void __launch_bounds__(128) knn_fixup_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4, FixList fix) {
     const unsigned n = *fix.count;
@@ -83,12 +97,16 @@ __global__ void __launch_bounds__(128) knn_fixup_kernel(Grid g, QueryView v, int
 }
 
 // ---- two-phase path for 2 <= k <= 32 ----
-// phase 1: distances only.  Ring 1 unclipped, every later ring clipped to the ball of the current k-th distance.
+// phase 1: distances only, over the 3x3x3 block (rows clipped progressively to the ball of the running k-th distance).
 // Every candidate that is not beyond the current k-th distance is also LOGGED (its position in the sorted array, 4 bytes,
 // slot-major shared memory): the final neighbours are a subset of the logged candidates (the k-th distance only shrinks),
 // and a query logs ~k(1 + ln(M/k)) of its M candidates, so phase 2 re-visits ~45 points instead of re-walking ~105.
-// Returns tau = exact k-th smallest d2 over the whole cloud (+inf if the cloud has fewer than k points), the block radius
-// R that proved it, and the number of logged candidates (> L means the log overflowed and is incomplete).
+// Returns tau = k-th smallest d2 inside the block (+inf if it holds fewer than k points), whether the block PROVES it
+// (tau < covered_d2(1)), and the number of logged candidates (> L means the log overflowed and is incomplete).
+// An unproved query (~18 % on the headline workload) still gets its row from the block, and is then listed for
+// knn_rings_kernel, which merges the outer rings into that row.  Measured on B200: growing rings inside this kernel cost
+// 1.3 ms of 4.7 ms because nearly every warp holds a few such queries and pays each 25-row pass with ~5 lanes active;
+// listed and compacted, the same queries run with all lanes busy.
 // launch shape per list size: 32 KB of log per block either way (64 slots x 128 threads, or 128 slots x 64 threads)
 #ifndef PCC_LOG16
 #define PCC_LOG16 48
@@ -104,25 +122,19 @@ __global__ void __launch_bounds__(128) knn_fixup_kernel(Grid g, QueryView v, int
 #endif
 template <int K> struct FastCfg { static constexpr int threads = 128, log_slots = K <= 16 ? PCC_LOG16 : PCC_LOG32, min_blocks = K <= 16 ? PCC_MB16 : PCC_MB32; };
 template <int K>
-__device__ __forceinline__ float kth_distance(const Grid &g, const QueryCell &c, float x, float y, float z, int k, RegDist<K> &list, int &R_out,
+__device__ __forceinline__ float kth_distance(const Grid &g, const QueryCell &c, float x, float y, float z, int k, RegDist<K> &list, bool &proved,
                                               uint32_t *__restrict__ slog, int &nlog) {
-    int Rin = -1, R = 1;
-    float kth = CUDART_INF_F;
-    for (;;) {
-        scan_progressive(g, c, Rin, R, [&]() { return to_cell_units(g, (k == K) ? list.d[K - 1] : list.at(k - 1)); }, [&](uint32_t pos, float4 p) {
-            const float d2 = dist2(x, y, z, p.x, p.y, p.z);
-            if (d2 <= list.d[K - 1]) {            // "<=": a candidate tied with the final k-th distance must be in the log too
-                if (nlog < FastCfg<K>::log_slots) slog[nlog * FastCfg<K>::threads] = pos;
-                ++nlog;
-                list.insert(d2);
-            }
-        });
-        kth = (k == K) ? list.d[K - 1] : list.at(k - 1);
-        const float cov = covered_d2(g, c, R);
-        if (cov == CUDART_INF_F || kth < cov) break;
-        Rin = R; R = next_ring(g, R, kth);
-    }
-    R_out = R;
+    scan_progressive(g, c, -1, 1, [&]() { return to_cell_units(g, (k == K) ? list.d[K - 1] : list.at(k - 1)); }, [&](uint32_t pos, float4 p) {
+        const float d2 = dist2(x, y, z, p.x, p.y, p.z);
+        if (d2 <= list.d[K - 1]) {            // "<=": a candidate tied with the final k-th distance must be in the log too
+            if (nlog < FastCfg<K>::log_slots) slog[nlog * FastCfg<K>::threads] = pos;
+            ++nlog;
+            list.insert(d2);
+        }
+    });
+    const float kth = (k == K) ? list.d[K - 1] : list.at(k - 1);
+    const float cov = covered_d2(g, c, 1);
+    proved = cov == CUDART_INF_F || kth < cov;
     return kth;
 }
 // measured on B200 (10 M queries, k = 16): 96 registers / 5 blocks per SM 6.44 ms, 79 / 6 blocks 5.85 ms, 64 / 8 blocks 5.51 ms --
@@ -136,6 +148,7 @@ __global__ void __launch_bounds__(FastCfg<K>::threads, FastCfg<K>::min_blocks) k
     float x, y, z; int64_t row; bool empty;
     const bool live = load_query(g, v, t, x, y, z, row, empty);
     if (!live) {
+        if (t < v.nq) fix.ring_flag[t] = 0;
         if (empty) { nkey_t e[K];
 #pragma unroll
             for (int j = 0; j < K; ++j) e[j] = PCC_EMPTY_KEY;
@@ -144,8 +157,8 @@ __global__ void __launch_bounds__(FastCfg<K>::threads, FastCfg<K>::min_blocks) k
     }
     const QueryCell c = locate(g, x, y, z);
     RegDist<K> list; list.init();
-    int R, nlog = 0;
-    const float tau = kth_distance<K>(g, c, x, y, z, k, list, R, slog, nlog);
+    int nlog = 0; bool proved;
+    const float tau = kth_distance<K>(g, c, x, y, z, k, list, proved, slog, nlog);
     // phase 2: keep the logged candidates with d2 <= tau (compacted in place: the m-th survivor never overtakes the read index)
     int m = 0;
     if (nlog <= kLogSlots) {
@@ -155,13 +168,14 @@ __global__ void __launch_bounds__(FastCfg<K>::threads, FastCfg<K>::min_blocks) k
             if (dist2(x, y, z, p.x, p.y, p.z) <= tau) { slog[m * kFastThreads] = pos; ++m; }
         }
     } else {
-        // log overflow (adversarial visiting order or heavy ties): re-walk the block of radius R inside the tau-ball instead
-        scan_clipped(g, c, -1, R, to_cell_units(g, tau), [&](uint32_t pos, float4 p) {
+        // log overflow (adversarial visiting order or heavy ties): re-walk the block inside the tau-ball instead
+        scan_clipped(g, c, -1, 1, to_cell_units(g, tau), [&](uint32_t pos, float4 p) {
             if (dist2(x, y, z, p.x, p.y, p.z) <= tau) { if (m < kLogSlots) slog[m * kFastThreads] = pos; ++m; }
         });
     }
-    if (fix.stats) { atomicAdd(fix.stats + 0, 1ull); atomicAdd(fix.stats + 1, (unsigned long long)nlog); atomicAdd(fix.stats + 4, R > 1 ? 1ull : 0ull); atomicAdd(fix.stats + 5, m > K ? 1ull : 0ull); atomicAdd(fix.stats + 6, (unsigned long long)m); atomicAdd(fix.stats + 3, nlog > kLogSlots ? 1ull : 0ull); }
-    if (m > K) { fix.list[atomicAdd(fix.count, 1u)] = (uint32_t)t; return; }      // more than K candidates tied at tau: exact path
+    if (fix.stats) { atomicAdd(fix.stats + 0, 1ull); atomicAdd(fix.stats + 1, (unsigned long long)nlog); atomicAdd(fix.stats + 4, proved ? 0ull : 1ull); atomicAdd(fix.stats + 5, m > K ? 1ull : 0ull); atomicAdd(fix.stats + 6, (unsigned long long)m); atomicAdd(fix.stats + 3, nlog > kLogSlots ? 1ull : 0ull); }
+    fix.ring_flag[t] = (m <= K && !proved) ? 1 : 0;
+    if (m > K) { push_list(fix.list, fix.count, (uint32_t)t); return; }           // more than K candidates tied at tau: exact path
     nkey_t e[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) {
@@ -170,6 +184,128 @@ __global__ void __launch_bounds__(FastCfg<K>::threads, FastCfg<K>::min_blocks) k
     }
     bitonic_sort_key<K>(e);
     write_row<K>(e, k, out_idx + row * k, out_d2 + row * k, vec4);
+}
+// Finishes the queries knn_fast_kernel could not prove inside the 3x3x3 block: the row it wrote holds the exact best
+// (d2, index) keys of that block, so it is loaded back as the starting list and the rings outside the block are merged in
+// until the k-th distance is covered.
+//
+// The work per query is heavy-tailed (most need four short runs just outside the block, 2 % need a 7x7x7 shell), and a
+// warp that walks "one query per lane, row by row" pays the maximum over its lanes at every step (measured: 1.7 ms for
+// 1.8 M queries).  So every LANE runs its own state machine and the loop body is one small uniform step:
+//   advance  -- a lane without points to walk tests up to kRowsPerStep rows of its pass and fetches the run bounds of the
+//               first row the ball of its k-th distance reaches,
+//   walk     -- a lane with a run in hand evaluates up to 4 of its points,
+//   settle   -- lanes that finished a pass (merge, cover test, next ring or write the row) or a query (take the next one
+//               from the list with one atomic per warp) do so together, once kSettleBatch lanes are waiting.
+// A pass normally only LOGS the points inside the ball of the k-th distance known when it starts (fp32 compare) and the
+// logged points are inserted with the exact 64-bit path when it settles; a pass that starts without k neighbours, or
+// overflows the log, INSERTS while walking instead and shrinks its ball as it goes.
+constexpr int kRingLog = 24, kRowsPerStep = 6, kSettleBatch = 8;
+#ifndef PCC_RINGS_MB
+#define PCC_RINGS_MB 4
+#endif
+template <int K>
+__global__ void __launch_bounds__(128, K <= 16 ? PCC_RINGS_MB : 3) knn_rings_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4, FixList fix) {
+    __shared__ uint32_t slog_all[kRingLog * 128];
+    uint32_t *slog = slog_all + threadIdx.x;
+    const unsigned n = *fix.ring_count, full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    // per-lane state
+    bool busy = false, exhausted = false, pass_done = false, inserting = false;
+    float x = 0.f, y = 0.f, z = 0.f, kth = CUDART_INF_F;
+    QueryCell c = {};
+    int Rin = 1, R = 2, az = 0, ay = 0, nlog = 0;
+    uint32_t j = 0, e = 0, j2 = 0, e2 = 0;
+    int32_t *oi = nullptr; float *od = nullptr;
+    RegList<K> list; list.init();
+    auto kth_of = [&]() { return key_d2((k == K) ? list.key[K - 1] : list.at(k - 1)); };
+    auto visit = [&](uint32_t pos, const float4 &p) {
+        const float d2 = dist2(x, y, z, p.x, p.y, p.z);
+        if (d2 <= kth) {
+            if (inserting) { list.offer(make_key(d2, __float_as_uint(p.w))); kth = kth_of(); }
+            else { if (nlog < kRingLog) slog[nlog * 128] = pos; ++nlog; }
+        }
+    };
+    for (;;) {
+        // ---- settle ----
+        const unsigned waiting = __ballot_sync(full, (busy && pass_done) || (!busy && !exhausted));
+        const unsigned walking = __ballot_sync(full, busy && !pass_done);
+        if (waiting == 0 && walking == 0) break;
+        if (waiting != 0 && (__popc(waiting) >= kSettleBatch || walking == 0)) {
+            if (busy && pass_done) {
+                bool again = false;
+                if (!inserting) {
+                    if (nlog <= kRingLog) {
+                        for (int q = 0; q < nlog; ++q) { const float4 p = __ldg(g.pts + slog[q * 128]); list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); }
+                        kth = kth_of();
+                    } else { inserting = true; again = true; }          // log overflow: same pass again, inserting while walking
+                }
+                if (!again) {
+                    const float cov = covered_d2(g, c, R);
+                    if (cov == CUDART_INF_F || kth < cov) { write_row<K>(list.key, k, oi, od, vec4); busy = false; }
+                    else { Rin = R; R = next_ring(g, R, kth); inserting = kth == CUDART_INF_F; }
+                }
+                az = ay = 0; nlog = 0; pass_done = false; j = e = j2 = e2 = 0;
+            }
+            const bool want = !busy && !exhausted;
+            const unsigned takers = __ballot_sync(full, want);
+            if (takers) {
+                unsigned base = 0;
+                if (lane == __ffs(takers) - 1) base = atomicAdd(fix.ring_cursor, (unsigned)__popc(takers));
+                base = __shfl_sync(full, base, __ffs(takers) - 1);
+                if (want) {
+                    const unsigned i = base + __popc(takers & ((1u << lane) - 1));
+                    int64_t row; bool empty;
+                    if (i >= n) exhausted = true;
+                    else if (load_query(g, v, (int64_t)fix.ring_list[i], x, y, z, row, empty)) {
+                        oi = out_idx + row * k; od = out_d2 + row * k;
+                        if (vec4 && K >= 4 && k == K) {
+#pragma unroll
+                            for (int t = 0; t + 3 < K; t += 4) {
+                                const int4 a = reinterpret_cast<const int4 *>(oi)[t >> 2]; const float4 d = reinterpret_cast<const float4 *>(od)[t >> 2];
+                                list.key[t] = a.x < 0 ? PCC_EMPTY_KEY : make_key(d.x, (uint32_t)a.x); list.key[t + 1] = a.y < 0 ? PCC_EMPTY_KEY : make_key(d.y, (uint32_t)a.y);
+                                list.key[t + 2] = a.z < 0 ? PCC_EMPTY_KEY : make_key(d.z, (uint32_t)a.z); list.key[t + 3] = a.w < 0 ? PCC_EMPTY_KEY : make_key(d.w, (uint32_t)a.w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < K; ++t) { list.key[t] = PCC_EMPTY_KEY; if (t < k) { const int32_t a = oi[t]; if (a >= 0) list.key[t] = make_key(od[t], (uint32_t)a); } }
+                        }
+                        c = locate(g, x, y, z);
+                        kth = kth_of();
+                        Rin = 1; R = next_ring(g, 1, kth); inserting = kth == CUDART_INF_F;
+                        az = ay = 0; nlog = 0; pass_done = false; j = e = j2 = e2 = 0;
+                        busy = true;
+                    }
+                }
+            }
+        }
+        // ---- advance: next run of this lane's pass ----
+        if (busy && !pass_done && j >= e) {
+            if (j2 < e2) { j = j2; e = e2; j2 = e2 = 0; }
+            else {
+                const int n1 = 2 * R + 1;
+                const float tau_u = to_cell_units(g, kth);
+#pragma unroll 1
+                for (int t = 0; t < kRowsPerStep; ++t) {
+                    if (az == n1) { pass_done = true; break; }
+                    const RowRuns r = row_runs(g, c, Rin, R, tau_u, az, ay);
+                    if (++ay == n1) { ay = 0; ++az; }
+                    if (r.j1 < r.e1) { j = r.j1; e = r.e1; j2 = r.j2; e2 = r.e2; break; }
+                    if (r.j2 < r.e2) { j = r.j2; e = r.e2; break; }
+                }
+            }
+        }
+        // ---- walk: up to four points of the run in hand ----
+        if (busy && j < e) {
+            const uint32_t last = e - 1;
+            const float4 p0 = __ldg(g.pts + j), p1 = __ldg(g.pts + min(j + 1, last)), p2 = __ldg(g.pts + min(j + 2, last)), p3 = __ldg(g.pts + min(j + 3, last));
+            visit(j, p0);
+            if (j + 1 < e) visit(j + 1, p1);
+            if (j + 2 < e) visit(j + 2, p2);
+            if (j + 3 < e) visit(j + 3, p3);
+            j += 4;
+        }
+    }
 }
 
 // ---- warp-owns-a-cell variant: the 3x3x3 stencil is staged in shared memory with TMA bulk copies ----
@@ -576,12 +712,21 @@ static void launch_knn_cell(const Grid &g, const QueryView &v, int k, int32_t *o
     PCC_LAUNCHED();
 }
 template <int K>
-static void launch_knn_fast(const Grid &g, const QueryView &v, int k, int32_t *oi, float *od, int vec4, FixList fix, cudaStream_t s) {
+static int launch_knn_fast(pcc_index *idx, const Grid &g, const QueryView &v, int k, int32_t *oi, float *od, int vec4, FixList fix, cudaStream_t s) {
+    size_t tmp = 0;
+    cub::DeviceSelect::Flagged(nullptr, tmp, cub::CountingInputIterator<uint32_t>(0), fix.ring_flag, fix.ring_list, fix.ring_count, (int)v.nq, s);
+    PCC_TRY(idx->cub_tmp.reserve(tmp));
     cudaMemsetAsync(fix.count, 0, sizeof(unsigned), s);
+    cudaMemsetAsync(fix.ring_cursor, 0, sizeof(unsigned), s);
     knn_fast_kernel<K><<<nblocks(v.nq, FastCfg<K>::threads), FastCfg<K>::threads, 0, s>>>(g, v, k, oi, od, vec4, fix);
+    PCC_LAUNCHED();
+    PCC_CUDA(cub::DeviceSelect::Flagged(idx->cub_tmp.p, tmp, cub::CountingInputIterator<uint32_t>(0), fix.ring_flag, fix.ring_list, fix.ring_count, (int)v.nq, s));
+    PCC_LAUNCHED();
+    knn_rings_kernel<K><<<148 * (K <= 16 ? PCC_RINGS_MB : 3), 128, 0, s>>>(g, v, k, oi, od, vec4, fix);
     PCC_LAUNCHED();
     knn_fixup_kernel<K><<<148 * 4, 128, 0, s>>>(g, v, k, oi, od, vec4, fix);
     PCC_LAUNCHED();
+    return PCC_OK;
 }
 
 }  // namespace pcc
@@ -628,12 +773,12 @@ static int knn_impl(pcc_index *idx, const void *q, int64_t nq, int stride_bytes,
         // per-thread walk even at 80 queries per cell (profiles/r1/cell_kernel_probe.jsonl), so it is never chosen automatically.
         const char *cell_env = getenv("PCC_CELL_KERNEL");
         const bool use_cell = cell_env && atoi(cell_env) != 0;
-        FixList fix{nullptr, nullptr, nullptr};
+        FixList fix{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
         if (k > 1 && k <= 32 && !exact_only) {
-            PCC_TRY(idx->misc.reserve((size_t)v.nq * 4 + 128));
-            fix.count = idx->misc.as<unsigned>();
-            fix.list = idx->misc.as<uint32_t>() + 32;
-            if (want_stats) { fix.stats = (unsigned long long *)(idx->misc.as<uint32_t>() + 2); PCC_CUDA(cudaMemsetAsync(fix.stats, 0, 64, s)); }
+            PCC_TRY(idx->misc.reserve((size_t)v.nq * 9 + 256));
+            fix.count = idx->misc.as<unsigned>(); fix.ring_count = fix.count + 1; fix.ring_cursor = fix.count + 30;
+            fix.list = idx->misc.as<uint32_t>() + 32; fix.ring_list = fix.list + v.nq; fix.ring_flag = (uint8_t *)(fix.ring_list + v.nq);
+            if (want_stats) { fix.stats = (unsigned long long *)(idx->misc.as<uint32_t>() + 2); PCC_CUDA(cudaMemsetAsync(fix.stats, 0, 112, s)); }
         }
         if (k == 1) launch_knn_reg<1>(g, v, k, oi, od, vec4, s);
         else if (exact_only && k <= 2) launch_knn_reg<2>(g, v, k, oi, od, vec4, s);
@@ -644,10 +789,10 @@ static int knn_impl(pcc_index *idx, const void *q, int64_t nq, int stride_bytes,
         else if (use_cell && k <= 8) launch_knn_cell<8>(g, v, k, oi, od, vec4, fix, s);
         else if (use_cell && k <= 16) launch_knn_cell<16>(g, v, k, oi, od, vec4, fix, s);
         else if (use_cell && k <= 32) launch_knn_cell<32>(g, v, k, oi, od, vec4, fix, s);
-        else if (k <= 4) launch_knn_fast<4>(g, v, k, oi, od, vec4, fix, s);
-        else if (k <= 8) launch_knn_fast<8>(g, v, k, oi, od, vec4, fix, s);
-        else if (k <= 16) launch_knn_fast<16>(g, v, k, oi, od, vec4, fix, s);
-        else if (k <= 32) launch_knn_fast<32>(g, v, k, oi, od, vec4, fix, s);
+        else if (k <= 4) PCC_TRY(launch_knn_fast<4>(idx, g, v, k, oi, od, vec4, fix, s));
+        else if (k <= 8) PCC_TRY(launch_knn_fast<8>(idx, g, v, k, oi, od, vec4, fix, s));
+        else if (k <= 16) PCC_TRY(launch_knn_fast<16>(idx, g, v, k, oi, od, vec4, fix, s));
+        else if (k <= 32) PCC_TRY(launch_knn_fast<32>(idx, g, v, k, oi, od, vec4, fix, s));
         else {
             const int th = heap_threads(k);
             PCC_TRY(set_heap_smem(knn_heap_kernel));
@@ -658,8 +803,8 @@ static int knn_impl(pcc_index *idx, const void *q, int64_t nq, int stride_bytes,
     }
     timer.stop();
     if (getenv("PCC_STATS") && k > 1 && k <= 32) {
-        unsigned long long h[8];
-        cudaMemcpyAsync(h, idx->misc.as<uint32_t>() + 2, 64, cudaMemcpyDeviceToHost, s); cudaStreamSynchronize(s);
+        unsigned long long h[14];
+        cudaMemcpyAsync(h, idx->misc.as<uint32_t>() + 2, 112, cudaMemcpyDeviceToHost, s); cudaStreamSynchronize(s);
         const double q = (double)std::max<unsigned long long>(h[0], 1);
         fprintf(stderr, "[pcc stats] queries=%llu logged/q=%.1f log_overflow=%.5f need_ring2=%.3f fixup=%.5f members/q=%.2f\n",
                 h[0], h[1] / q, h[3] / q, h[4] / q, h[5] / q, h[6] / q);

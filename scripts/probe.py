@@ -4,6 +4,8 @@ import os, sys, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from pointcloudcomparator_b200 import synth
+from pointcloudcomparator_b200 import _lib
+_lib.SO_PATH = os.path.abspath(os.environ.get("PCC_SO", _lib.SO_PATH))          # developer builds from scripts/build_variant.sh
 from pointcloudcomparator_b200.search import GridSearch
 
 n = int(sys.argv[1]); kind = sys.argv[2]; ks = [int(v) for v in sys.argv[3].split(",")]; occs = [float(v) for v in sys.argv[4].split(",")]
