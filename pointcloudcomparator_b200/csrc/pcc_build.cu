@@ -92,6 +92,27 @@ __global__ void inverse_kernel(const float4 *__restrict__ pts, int64_t n, uint32
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) inv_pos[__float_as_int(pts[i].w)] = (uint32_t)i;
 }
+// occ bit c = cell c is not empty.  The dense cell_start table is far larger than L2 on big grids (56 M cells = 225 MB at
+// the 10 M-point headline size) while the bitmap is 7 MB, so the ring passes that mostly verify EMPTY cells around a block
+// test the bitmap first and touch cell_start only where there is something to read.
+__global__ void occupancy_kernel(const uint32_t *__restrict__ cell_start, int64_t n_cells, uint32_t *__restrict__ occ) {
+    const int64_t words = (n_cells + 31) / 32 + 1;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < words * 32; c += (int64_t)gridDim.x * blockDim.x) {
+        const bool full = c < n_cells && cell_start[c + 1] > cell_start[c];
+        const unsigned w = __ballot_sync(0xffffffffu, full);
+        if ((threadIdx.x & 31) == 0) occ[c >> 5] = w;
+    }
+}
+int rebuild_occupancy(pcc_index *idx, cudaStream_t s) {
+    const int64_t n_cells = std::max<int64_t>(idx->gh.n_cells, 1);
+    PCC_TRY(idx->occ.reserve((size_t)((n_cells + 31) / 32 + 1) * 4));
+    const int64_t threads = ((n_cells + 31) / 32 + 1) * 32;
+    occupancy_kernel<<<(unsigned)std::min<int64_t>((threads + 255) / 256, 148 * 32), 256, 0, s>>>(idx->cell_start.as<uint32_t>(), idx->gh.n_cells, idx->occ.as<uint32_t>());
+    PCC_LAUNCHED();
+    PCC_CUDA(cudaGetLastError());
+    idx->occ_valid = true;
+    return PCC_OK;
+}
 int rebuild_inverse(pcc_index *idx, cudaStream_t s) {
     PCC_TRY(idx->inv_pos.reserve((size_t)std::max<int64_t>(idx->n_input, 1) * 4));
     PCC_CUDA(cudaMemsetAsync(idx->inv_pos.p, 0xFF, (size_t)std::max<int64_t>(idx->n_input, 1) * 4, s));
@@ -121,7 +142,12 @@ static double occupancy_target(int k_hint) {
     const char *e = getenv("PCC_OCC");
     if (e && atof(e) > 0) return atof(e);
     int k = k_hint > 0 ? k_hint : 16;
-    return std::max(1.0, 0.5 * k);    // 3x3x3 block holds the k nearest for ~80-90 % of queries; the rest take a ball-clipped ring 2
+    if (k == 1) return 1.0;
+    // Measured on B200 (10 M queries on a 10 M-point surface cloud, kNN ms at target 4 / 6 / 8 / 10 / 12): k = 4: 3.46 / 2.60 /
+    // 2.21 / - / -, k = 8: 4.31 / 3.14 / 2.71 / 2.76 / -, k = 16: - / 4.89 / 4.13 / 4.17 / 4.15, k = 32 at 12 / 16 / 20: 9.47 / 9.52 /
+    // 10.4.  With ~8 points per occupied cell the 3x3x3 block settles >80 % of the queries for k <= 16; smaller cells send too
+    // many of them to the ring passes, larger ones make the block walk longer.
+    return std::max(8.0, 0.5 * k);
 }
 
 static void dims_for(const double ext[3], double cell, int dims[3]) {
@@ -217,7 +243,7 @@ void pcc_destroy(pcc_index *idx) {
     cudaSetDevice(idx->device);
     if (idx->shadow) { pcc_index *sh = idx->shadow; idx->shadow = nullptr; pcc_destroy(sh); }
     for (int i = 0; i < 2; ++i) if (idx->pipe_stream[i]) cudaStreamDestroy(idx->pipe_stream[i]);
-    Buf *bufs[] = {&idx->pts, &idx->cell_start, &idx->raw, &idx->stage4, &idx->cellrank, &idx->qbuf, &idx->qkeys, &idx->qkeys2, &idx->qperm, &idx->qperm2,
+    Buf *bufs[] = {&idx->pts, &idx->cell_start, &idx->occ, &idx->raw, &idx->stage4, &idx->cellrank, &idx->qbuf, &idx->qkeys, &idx->qkeys2, &idx->qperm, &idx->qperm2,
                    &idx->cub_tmp, &idx->out_i, &idx->out_f, &idx->out_l, &idx->keys64, &idx->keys64b, &idx->misc, &idx->parent, &idx->inv_pos};
     for (Buf *b : bufs) b->release();
     if (idx->h_pinned) cudaFreeHost(idx->h_pinned);
@@ -246,6 +272,7 @@ int pcc_build(pcc_index *idx, const void *pts, int64_t n, int stride_bytes, cons
     PCC_CUDA(cudaSetDevice(idx->device));
     idx->built = false;
     idx->inv_valid = false;
+    idx->occ_valid = false;
     const int64_t m = indices ? n_idx : n;
     idx->n_input = n;                 // labels / self-query rows are addressed by ORIGINAL row number
     idx->n_indexed = 0;
@@ -287,6 +314,8 @@ int pcc_build(pcc_index *idx, const void *pts, int64_t n, int stride_bytes, cons
         PCC_TRY(idx->pts.reserve(sizeof(float4)));
         PCC_TRY(idx->cell_start.reserve(2 * sizeof(uint32_t)));
         PCC_CUDA(cudaMemsetAsync(idx->cell_start.p, 0, 2 * sizeof(uint32_t), s));
+        idx->gh = GridHost();
+        PCC_TRY(rebuild_occupancy(idx, s));
         idx->built = true;
         return PCC_OK;
     }
@@ -356,6 +385,7 @@ int pcc_build(pcc_index *idx, const void *pts, int64_t n, int stride_bytes, cons
     scatter_kernel<<<blocks_for(m, 256), 256, 0, s>>>(idx->stage4.as<float4>(), idx->cellrank.as<uint2>(), m, idx->cell_start.as<uint32_t>(), idx->pts.as<float4>());
     PCC_LAUNCHED();
     PCC_CUDA(cudaGetLastError());
+    PCC_TRY(rebuild_occupancy(idx, s));
     if (mem == PCC_HOST) PCC_CUDA(cudaStreamSynchronize(s));
     idx->built = true;
     return PCC_OK;
@@ -384,6 +414,7 @@ int pcc_adopt(pcc_index *idx, const double meta[16], void *stream) {
     PCC_TRY(idx->cell_start.reserve((size_t)(idx->gh.n_cells + 1) * sizeof(uint32_t)));
     idx->built = true;
     idx->inv_valid = false;
+    idx->occ_valid = false;       // the caller fills the arrays after this call: the bitmap is derived on the first query
     return PCC_OK;
 }
 

@@ -14,6 +14,7 @@ namespace pcc {
 struct Grid {
     const float4 *pts;            // sorted by cell; .w = original index (int bits)
     const uint32_t *cell_start;   // n_cells + 1
+    const uint32_t *occ;          // n_cells bits (+ one padding word): cell holds at least one point
     float ox, oy, oz;             // origin = bbox min
     float inv_cell, cell;
     int nx, ny, nz;
@@ -120,6 +121,17 @@ __device__ __forceinline__ void walk_run(const Grid &g, uint32_t j, uint32_t e, 
 // tightens early and fewer later candidates pass the insertion guard.
 __device__ __forceinline__ int centre_out(int a) { return (a & 1) ? -((a + 1) >> 1) : (a >> 1); }
 struct RowRuns { uint32_t j1, e1, j2, e2; };
+// does any of the cells [xa, xb] of the row whose first cell has linear index `base` hold a point?  One bit per cell
+// (Grid::occ); ranges longer than 32 cells are not tested.  Rings beyond the first mostly verify EMPTY cells, and the
+// bitmap answers that from L1/L2 where the dense cell_start table (32x larger) would go to DRAM.
+__device__ __forceinline__ bool row_occupied(const Grid &g, size_t base, int xa, int xb) {
+    if (xb - xa >= 32) return true;
+    const size_t b = base + (size_t)xa;
+    const uint32_t w0 = __ldg(g.occ + (b >> 5)), w1 = __ldg(g.occ + (b >> 5) + 1);
+    const uint32_t bits = __funnelshift_r(w0, w1, (uint32_t)(b & 31));
+    const int len = xb - xa + 1;
+    return (bits & (len == 32 ? 0xffffffffu : ((1u << len) - 1u))) != 0u;
+}
 // run bounds of row (az, ay) of the block (centre-out numbering); empty runs (j == e) for skipped rows
 __device__ __forceinline__ RowRuns row_runs(const Grid &g, const QueryCell &c, int Rin, int Rout, float tau_u, int az, int ay) {
     RowRuns r; r.j1 = r.e1 = r.j2 = r.e2 = 0;
@@ -135,14 +147,16 @@ __device__ __forceinline__ RowRuns row_runs(const Grid &g, const QueryCell &c, i
         xlo = max(xlo, (int)floorf(c.ux - w)); xhi = min(xhi, (int)floorf(c.ux + w));
     }
     xlo = max(xlo, 0); xhi = min(xhi, g.nx - 1);
-    const uint32_t *row = g.cell_start + ((size_t)z * g.ny + y) * g.nx;
+    const size_t base = ((size_t)z * g.ny + y) * g.nx;
+    const uint32_t *row = g.cell_start + base;
+    const bool probe = Rin >= 0;                     // first pass (whole block): the table rows are hot, read them directly
     if (max(abs(dz), abs(dy)) > Rin) {
-        if (xlo <= xhi) { r.j1 = __ldg(row + xlo); r.e1 = __ldg(row + xhi + 1); }
+        if (xlo <= xhi && (!probe || row_occupied(g, base, xlo, xhi))) { r.j1 = __ldg(row + xlo); r.e1 = __ldg(row + xhi + 1); }
     } else {
         const int xl = min(xhi, c.cx - Rin - 1);     // left strip [xlo, xl]
-        if (xlo <= xl) { r.j1 = __ldg(row + xlo); r.e1 = __ldg(row + xl + 1); }
+        if (xlo <= xl && row_occupied(g, base, xlo, xl)) { r.j1 = __ldg(row + xlo); r.e1 = __ldg(row + xl + 1); }
         const int xr = max(xlo, c.cx + Rin + 1);     // right strip [xr, xhi]
-        if (xr <= xhi) { r.j2 = __ldg(row + xr); r.e2 = __ldg(row + xhi + 1); }
+        if (xr <= xhi && row_occupied(g, base, xr, xhi)) { r.j2 = __ldg(row + xr); r.e2 = __ldg(row + xhi + 1); }
     }
     return r;
 }

@@ -62,6 +62,8 @@ struct pcc_index {
     pcc::GridHost gh;
     pcc::Buf pts;             // float4 [n_indexed], sorted by cell
     pcc::Buf cell_start;      // uint32 [n_cells + 1]
+    pcc::Buf occ;             // uint32 [n_cells / 32 + 2]: one bit per cell, set when the cell holds a point (derived from cell_start)
+    bool occ_valid = false;
     // scratch (grow-only, reused by every call on this index; calls on one index are serialised by the caller per stream)
     pcc::Buf raw, stage4, cellrank, qbuf, qkeys, qkeys2, qperm, qperm2, cub_tmp, out_i, out_f, out_l, keys64, keys64b, misc, parent, inv_pos;
     bool inv_valid = false;   // inv_pos (original row -> sorted position) is built lazily by the consumers that need it
@@ -80,7 +82,7 @@ struct pcc_index {
     pcc::Grid grid() const {
         const pcc_index *o = grid_owner ? grid_owner : this;
         pcc::Grid g;
-        g.pts = o->pts.as<float4>(); g.cell_start = o->cell_start.as<uint32_t>();
+        g.pts = o->pts.as<float4>(); g.cell_start = o->cell_start.as<uint32_t>(); g.occ = o->occ.as<uint32_t>();
         g.ox = o->gh.ox; g.oy = o->gh.oy; g.oz = o->gh.oz; g.inv_cell = o->gh.inv_cell; g.cell = o->gh.cell;
         g.nx = o->gh.nx; g.ny = o->gh.ny; g.nz = o->gh.nz; g.n = (uint32_t)o->n_indexed;
         return g;
@@ -99,6 +101,7 @@ struct Queries {
 int prepare_queries(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int mem, cudaStream_t s, Queries *out);
 int copy_out(void *dst, const void *src_dev, size_t bytes, int mem, cudaStream_t s);
 int rebuild_inverse(pcc_index *idx, cudaStream_t s);
+int rebuild_occupancy(pcc_index *idx, cudaStream_t s);   // occ bitmap from cell_start (after pcc_build / pcc_adopt)
 struct KernelTimer {
     pcc_index *idx; cudaStream_t s;
     KernelTimer(pcc_index *i, cudaStream_t st) : idx(i), s(st) { if (idx->timing) cudaEventRecord(idx->ev0, s); }

@@ -77,10 +77,11 @@ template <int K>
 __global__ void __launch_bounds__(128) knn_reg_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4) {
     knn_reg_body<K>(g, v, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, k, out_idx, out_d2, vec4);
 }
+constexpr unsigned kTiedToWide = 4096;   // a tied-query list this short is finished by knn_wide_kernel instead of knn_fixup_kernel
 // queries the fast path could not prove exact (listed by knn_fast_kernel)
 // `ring_flag[t]` = 1 for the queries whose 3x3x3 block did not prove the k-th distance; a stream compaction turns the flags
 // into `ring_list` / `ring_count` IN PROCESSING ORDER (neighbouring lanes stay neighbours in space) for knn_rings_kernel.
-struct FixList { uint32_t *list; unsigned *count; unsigned long long *stats; uint32_t *ring_list; unsigned *ring_count; uint8_t *ring_flag; unsigned *ring_cursor; };   // stats: optional debug counters (PCC_STATS=1)
+struct FixList { uint32_t *list; unsigned *count; unsigned long long *stats; uint32_t *ring_list; unsigned *ring_count; uint8_t *ring_flag; uint32_t *wide_list; unsigned *wide_count; };   // stats: optional debug counters (PCC_STATS=1)
 // append `value` to a device list, one atomic per warp
 __device__ __forceinline__ void push_list(uint32_t *list, unsigned *count, uint32_t value) {
     const unsigned mask = __activemask();
@@ -93,6 +94,7 @@ __device__ __forceinline__ void push_list(uint32_t *list, unsigned *count, uint3
 template <int K>
 __global__ void __launch_bounds__(128) knn_fixup_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4, FixList fix) {
     const unsigned n = *fix.count;
+    if (fix.wide_list && n <= kTiedToWide) return;          // a short list was taken by knn_wide_kernel
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) knn_reg_body<K>(g, v, (int64_t)fix.list[i], k, out_idx, out_d2, vec4);
 }
 
@@ -120,11 +122,12 @@ __global__ void __launch_bounds__(128) knn_fixup_kernel(Grid g, QueryView v, int
 #ifndef PCC_MB32
 #define PCC_MB32 5
 #endif
+constexpr int kRingMaxR = 3;      // widest block knn_rings_kernel settles; beyond that a query is "wide" (knn_wide_kernel)
 template <int K> struct FastCfg { static constexpr int threads = 128, log_slots = K <= 16 ? PCC_LOG16 : PCC_LOG32, min_blocks = K <= 16 ? PCC_MB16 : PCC_MB32; };
 template <int K>
 __device__ __forceinline__ float kth_distance(const Grid &g, const QueryCell &c, float x, float y, float z, int k, RegDist<K> &list, bool &proved,
-                                              uint32_t *__restrict__ slog, int &nlog) {
-    scan_progressive(g, c, -1, 1, [&]() { return to_cell_units(g, (k == K) ? list.d[K - 1] : list.at(k - 1)); }, [&](uint32_t pos, float4 p) {
+                                              uint32_t *__restrict__ slog, int &nlog, const int R0) {
+    scan_progressive(g, c, -1, R0, [&]() { return to_cell_units(g, (k == K) ? list.d[K - 1] : list.at(k - 1)); }, [&](uint32_t pos, float4 p) {
         const float d2 = dist2(x, y, z, p.x, p.y, p.z);
         if (d2 <= list.d[K - 1]) {            // "<=": a candidate tied with the final k-th distance must be in the log too
             if (nlog < FastCfg<K>::log_slots) slog[nlog * FastCfg<K>::threads] = pos;
@@ -133,22 +136,21 @@ __device__ __forceinline__ float kth_distance(const Grid &g, const QueryCell &c,
         }
     });
     const float kth = (k == K) ? list.d[K - 1] : list.at(k - 1);
-    const float cov = covered_d2(g, c, 1);
+    const float cov = covered_d2(g, c, R0);
     proved = cov == CUDART_INF_F || kth < cov;
     return kth;
 }
-// measured on B200 (10 M queries, k = 16): 96 registers / 5 blocks per SM 6.44 ms, 79 / 6 blocks 5.85 ms, 64 / 8 blocks 5.51 ms --
-// the kernel is latency- and issue-bound, so occupancy is worth a few spilled words
+// One query through the two-phase path over the block of radius R0 (= 1) around its cell.  An unproved query is flagged
+// for knn_rings_kernel when one more ring can settle it (its row is written first); otherwise it is listed as "wide" for
+// knn_wide_kernel.  More than K candidates tied at the k-th distance -> the exact per-thread kernel.
 template <int K>
-__global__ void __launch_bounds__(FastCfg<K>::threads, FastCfg<K>::min_blocks) knn_fast_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4, FixList fix) {
+__device__ __forceinline__ void knn_fast_body(const Grid &g, const QueryView &v, const int64_t t, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4,
+                                              const FixList &fix, uint32_t *__restrict__ slog, const int R0) {
     constexpr int kFastThreads = FastCfg<K>::threads, kLogSlots = FastCfg<K>::log_slots;
-    __shared__ uint32_t slog_all[kLogSlots * kFastThreads];
-    uint32_t *slog = slog_all + threadIdx.x;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float x, y, z; int64_t row; bool empty;
     const bool live = load_query(g, v, t, x, y, z, row, empty);
     if (!live) {
-        if (t < v.nq) fix.ring_flag[t] = 0;
+        if (R0 == 1 && t < v.nq) fix.ring_flag[t] = 0;
         if (empty) { nkey_t e[K];
 #pragma unroll
             for (int j = 0; j < K; ++j) e[j] = PCC_EMPTY_KEY;
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(FastCfg<K>::threads, FastCfg<K>::min_blocks) k
     const QueryCell c = locate(g, x, y, z);
     RegDist<K> list; list.init();
     int nlog = 0; bool proved;
-    const float tau = kth_distance<K>(g, c, x, y, z, k, list, proved, slog, nlog);
+    const float tau = kth_distance<K>(g, c, x, y, z, k, list, proved, slog, nlog, R0);
     // phase 2: keep the logged candidates with d2 <= tau (compacted in place: the m-th survivor never overtakes the read index)
     int m = 0;
     if (nlog <= kLogSlots) {
@@ -169,13 +171,19 @@ __global__ void __launch_bounds__(FastCfg<K>::threads, FastCfg<K>::min_blocks) k
         }
     } else {
         // log overflow (adversarial visiting order or heavy ties): re-walk the block inside the tau-ball instead
-        scan_clipped(g, c, -1, 1, to_cell_units(g, tau), [&](uint32_t pos, float4 p) {
+        scan_clipped(g, c, -1, R0, to_cell_units(g, tau), [&](uint32_t pos, float4 p) {
             if (dist2(x, y, z, p.x, p.y, p.z) <= tau) { if (m < kLogSlots) slog[m * kFastThreads] = pos; ++m; }
         });
     }
-    if (fix.stats) { atomicAdd(fix.stats + 0, 1ull); atomicAdd(fix.stats + 1, (unsigned long long)nlog); atomicAdd(fix.stats + 4, proved ? 0ull : 1ull); atomicAdd(fix.stats + 5, m > K ? 1ull : 0ull); atomicAdd(fix.stats + 6, (unsigned long long)m); atomicAdd(fix.stats + 3, nlog > kLogSlots ? 1ull : 0ull); }
-    fix.ring_flag[t] = (m <= K && !proved) ? 1 : 0;
-    if (m > K) { push_list(fix.list, fix.count, (uint32_t)t); return; }           // more than K candidates tied at tau: exact path
+    if (fix.stats && R0 == 1) { atomicAdd(fix.stats + 0, 1ull); atomicAdd(fix.stats + 1, (unsigned long long)nlog); atomicAdd(fix.stats + 4, proved ? 0ull : 1ull); atomicAdd(fix.stats + 5, m > K ? 1ull : 0ull); atomicAdd(fix.stats + 6, (unsigned long long)m); atomicAdd(fix.stats + 3, nlog > kLogSlots ? 1ull : 0ull); }
+    // where an unproved query goes next: one more ring (flag), the wide pass, or the exact kernel
+    const bool tied = m > K;                                                       // more than K candidates tied at tau: exact path
+    const bool wide = !tied && !proved && (tau == CUDART_INF_F || next_ring(g, 1, tau) > kRingMaxR);
+#ifndef PCC_X_NOFLAG
+    if (R0 == 1) fix.ring_flag[t] = (!tied && !proved && !wide) ? 1 : 0;
+#endif
+    if (tied) { push_list(fix.list, fix.count, (uint32_t)t); return; }
+    if (wide) { push_list(fix.wide_list, fix.wide_count, (uint32_t)t); return; }
     nkey_t e[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) {
@@ -185,126 +193,262 @@ __global__ void __launch_bounds__(FastCfg<K>::threads, FastCfg<K>::min_blocks) k
     bitonic_sort_key<K>(e);
     write_row<K>(e, k, out_idx + row * k, out_d2 + row * k, vec4);
 }
-// Finishes the queries knn_fast_kernel could not prove inside the 3x3x3 block: the row it wrote holds the exact best
-// (d2, index) keys of that block, so it is loaded back as the starting list and the rings outside the block are merged in
-// until the k-th distance is covered.
-//
-// The work per query is heavy-tailed (most need four short runs just outside the block, 2 % need a 7x7x7 shell), and a
-// warp that walks "one query per lane, row by row" pays the maximum over its lanes at every step (measured: 1.7 ms for
-// 1.8 M queries).  So every LANE runs its own state machine and the loop body is one small uniform step:
-//   advance  -- a lane without points to walk tests up to kRowsPerStep rows of its pass and fetches the run bounds of the
-//               first row the ball of its k-th distance reaches,
-//   walk     -- a lane with a run in hand evaluates up to 4 of its points,
-//   settle   -- lanes that finished a pass (merge, cover test, next ring or write the row) or a query (take the next one
-//               from the list with one atomic per warp) do so together, once kSettleBatch lanes are waiting.
-// A pass normally only LOGS the points inside the ball of the k-th distance known when it starts (fp32 compare) and the
-// logged points are inserted with the exact 64-bit path when it settles; a pass that starts without k neighbours, or
-// overflows the log, INSERTS while walking instead and shrinks its ball as it goes.
-constexpr int kRingLog = 24, kRowsPerStep = 6, kSettleBatch = 8;
+// measured on B200 (10 M queries, k = 16): 96 registers / 5 blocks per SM 6.44 ms, 79 / 6 blocks 5.85 ms, 64 / 8 blocks 5.51 ms --
+// the kernel is latency- and issue-bound, so occupancy is worth a few spilled words
+template <int K>
+__global__ void __launch_bounds__(FastCfg<K>::threads, FastCfg<K>::min_blocks) knn_fast_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4, FixList fix) {
+    __shared__ uint32_t slog_all[FastCfg<K>::log_slots * FastCfg<K>::threads];
+    knn_fast_body<K>(g, v, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, k, out_idx, out_d2, vec4, fix, slog_all + threadIdx.x, 1);
+}
+// The "wide" queries (fewer than k points in the 3x3x3 block, a ball wider than two cells, or whatever knn_rings_kernel
+// could not settle): few, but each needs many rows -- as one thread per query they are a serial chain of dependent loads
+// hundreds of rows long (measured: 35 k such queries cost 0.9 ms).  Here ONE WARP owns a query.  A pass takes its rows 32
+// at a time: each lane plans one row (run bounds), the occupied runs are appended to a run list with their length prefix
+// sums, and the points of all listed runs are then dealt round-robin to the lanes (point q -> lane q % 32), so every lane
+// is busy whatever the run lengths.  Points inside the current ball are appended (ballot + prefix count) to a per-warp
+// buffer of 64-bit (d2, index) keys in shared memory; when the buffer fills up the k smallest keys are extracted by
+// repeated warp-wide minimum, which also tightens the ball.  Passes grow ring by ring exactly like the per-thread search
+// (covered_d2 / next_ring), so the result is exact for any density.
+constexpr int kWideCap = 128;                    // keys per warp buffer (4 per lane)
+__device__ __forceinline__ nkey_t warp_min_key(nkey_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const nkey_t w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; }
+    return v;
+}
+// k smallest of buf[0, cnt) -> buf[0, min(cnt, k)) ascending; returns the new count
+__device__ __forceinline__ int wide_truncate(nkey_t *buf, int cnt, int k, int lane) {
+    nkey_t v[kWideCap / 32];
+#pragma unroll
+    for (int i = 0; i < kWideCap / 32; ++i) v[i] = (lane + 32 * i) < cnt ? buf[lane + 32 * i] : PCC_EMPTY_KEY;
+    __syncwarp();
+    const int keep = min(cnt, k);
+    nkey_t mine = PCC_EMPTY_KEY;
+    for (int it = 0; it < keep; ++it) {
+        nkey_t m = v[0];
+#pragma unroll
+        for (int i = 1; i < kWideCap / 32; ++i) m = v[i] < m ? v[i] : m;
+        const nkey_t best = warp_min_key(m);
+#pragma unroll
+        for (int i = 0; i < kWideCap / 32; ++i) if (v[i] == best) v[i] = PCC_EMPTY_KEY;      // keys are unique (one per point)
+        if (lane == it) mine = best;
+    }
+    if (lane < keep) buf[lane] = mine;
+    __syncwarp();
+    return keep;
+}
+constexpr int kWideRuns = 64;                    // runs planned per chunk of 32 rows (two strips per row at most)
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t w = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += w; }
+    return v;
+}
+__global__ void __launch_bounds__(128, 4) knn_wide_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, FixList fix) {
+    __shared__ nkey_t sbuf[4 * kWideCap];
+    __shared__ uint32_t srun_j[4 * kWideRuns], srun_len[4 * kWideRuns], srun_off[4 * (kWideRuns + 1)];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    nkey_t *buf = sbuf + wib * kWideCap;
+    uint32_t *run_j = srun_j + wib * kWideRuns, *run_len = srun_len + wib * kWideRuns, *run_off = srun_off + wib * (kWideRuns + 1);
+    // a SHORT list of tied queries (more than K candidates at the k-th distance) is taken along: as a handful of single
+    // threads in knn_fixup_kernel they are a 0.1 ms latency tail; a long one (lattice data) stays with that kernel
+    const unsigned n_wide = *fix.wide_count, n_tied = *fix.count <= kTiedToWide ? *fix.count : 0u, n = n_wide + n_tied;
+    const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
+    for (unsigned i = blockIdx.x * 4 + wib; i < n; i += gridDim.x * 4) {
+        float x, y, z; int64_t row; bool empty;
+        if (!load_query(g, v, (int64_t)(i < n_wide ? fix.wide_list[i] : fix.list[i - n_wide]), x, y, z, row, empty)) continue;      // warp-uniform
+        const QueryCell c = locate(g, x, y, z);
+        int cnt = 0, Rin = -1, R = 3;            // a listed query is known not to be settled by the 3x3x3 block
+        float tau = CUDART_INF_F;
+        unsigned long long steps = 0;
+        for (;;) {
+            const int n1 = 2 * R + 1, nrows = n1 * n1;
+            const float tau_u = to_cell_units(g, tau);
+            for (int row0 = 0; row0 < nrows; row0 += 32) {
+                // plan: one row per lane -> occupied runs, appended to the warp's run list
+                RowRuns r; r.j1 = r.e1 = r.j2 = r.e2 = 0;
+                if (row0 + lane < nrows) r = row_runs(g, c, Rin, R, tau_u, (row0 + lane) / n1, (row0 + lane) % n1);
+                const unsigned m1 = __ballot_sync(full, r.j1 < r.e1), m2 = __ballot_sync(full, r.j2 < r.e2);
+                const int nrun = __popc(m1) + __popc(m2);
+                if (nrun == 0) continue;
+                if (r.j1 < r.e1) { const int q = __popc(m1 & lt); run_j[q] = r.j1; run_len[q] = r.e1 - r.j1; }
+                if (r.j2 < r.e2) { const int q = __popc(m1) + __popc(m2 & lt); run_j[q] = r.j2; run_len[q] = r.e2 - r.j2; }
+                __syncwarp();
+                const uint32_t la = lane < nrun ? run_len[lane] : 0u, lb = lane + 32 < nrun ? run_len[lane + 32] : 0u;
+                const uint32_t ia = warp_inclusive_scan(la, lane), ib = warp_inclusive_scan(lb, lane);
+                const uint32_t ta = __shfl_sync(full, ia, 31), P = ta + __shfl_sync(full, ib, 31);
+                run_off[lane] = ia - la; run_off[lane + 32] = ta + ib - lb;
+                if (lane == 0) run_off[kWideRuns] = P;
+                __syncwarp();
+                // flat walk: point q of the concatenated runs belongs to lane q % 32 -- every lane busy whatever the run lengths
+                int rc = 0;
+                for (uint32_t q0 = 0; q0 < P; q0 += 32) {
+                    const uint32_t q = q0 + lane;
+                    bool has = false; nkey_t key = PCC_EMPTY_KEY;
+                    if (q < P) {
+                        while (q >= run_off[rc + 1]) ++rc;
+                        const float4 p = __ldg(g.pts + run_j[rc] + (q - run_off[rc]));
+                        const float d2 = dist2(x, y, z, p.x, p.y, p.z);
+                        has = d2 <= tau; key = make_key(d2, __float_as_uint(p.w));
+                    }
+                    const unsigned hit = __ballot_sync(full, has);
+                    if (hit) {
+                        if (has) buf[cnt + __popc(hit & lt)] = key;
+                        cnt += __popc(hit);
+                        __syncwarp();
+                        if (cnt > kWideCap - 32) {
+                            cnt = wide_truncate(buf, cnt, k, lane);
+                            if (cnt == k) tau = key_d2(buf[k - 1]);        // later points must beat (or tie) the k-th key
+                        }
+                    }
+                    ++steps;
+                }
+                __syncwarp();
+            }
+            cnt = wide_truncate(buf, cnt, k, lane);
+            const float kth = cnt == k ? key_d2(buf[k - 1]) : CUDART_INF_F;
+            tau = kth;
+            const float cov = covered_d2(g, c, R);
+            if (cov == CUDART_INF_F || kth < cov) break;
+            Rin = R; R = next_ring(g, R, kth);
+        }
+        if (fix.stats && lane == 0) { atomicAdd(fix.stats + 2, 1ull); atomicAdd(fix.stats + 7, steps); atomicAdd(fix.stats + 8 + (R <= 1 ? 0 : R == 2 ? 1 : R == 3 ? 2 : R < 8 ? 3 : R < 16 ? 4 : 5), 1ull); }
+        if (lane < k) {
+            const nkey_t key = lane < cnt ? buf[lane] : PCC_EMPTY_KEY;
+            out_idx[row * k + lane] = key_idx(key); out_d2[row * k + lane] = key_d2(key);
+        }
+        __syncwarp();
+    }
+}
+// Finishes the queries knn_fast_kernel could not prove inside the 3x3x3 block and whose ball fits a block of radius
+// kRingMaxR.  One thread per listed query (the list is in processing order, so the lanes of a warp are neighbours in
+// space).  The kernel is bound by load latency, not by arithmetic, so the work is cut into stages whose loads are
+// independent of each other and issued four at a time:
+//   plan   -- (no loads) the rows outside the block that the ball of the k-th distance reaches -- a clipped box, not all 25
+//             or 49 -- and their x-ranges, packed into the thread's log column,
+//   probe  -- the occupancy bitmap for each range: most of those cells are EMPTY and are dismissed here without touching
+//             the (32x larger, DRAM-resident) cell table; the occupied ranges go to the thread's run table,
+//   bounds -- the cell_start pair of every run,
+//   walk   -- the points of the runs, four per step across run boundaries; those inside the ball are logged.
+// Only the k-th distance of the row the fast kernel wrote is read up front.  If nothing was logged (the usual outcome: the
+// ball pokes into empty space) the row already is the answer; otherwise the row is loaded, the logged points are
+// inserted with the exact 64-bit path and the row is rewritten.  Whatever does not fit this shape (fewer than k points in
+// the block, more ranges or logged points than the tables hold, not proved afterwards) goes to knn_wide_kernel.
+constexpr int kRingLog = 24, kRingRuns = 12;
 #ifndef PCC_RINGS_MB
-#define PCC_RINGS_MB 4
+#define PCC_RINGS_MB 6
 #endif
 template <int K>
-__global__ void __launch_bounds__(128, K <= 16 ? PCC_RINGS_MB : 3) knn_rings_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4, FixList fix) {
+__global__ void __launch_bounds__(128, K <= 16 ? PCC_RINGS_MB : 4) knn_rings_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4, FixList fix) {
     __shared__ uint32_t slog_all[kRingLog * 128];
+    __shared__ uint2 srun_all[kRingRuns * 128];
     uint32_t *slog = slog_all + threadIdx.x;
-    const unsigned n = *fix.ring_count, full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    // per-lane state
-    bool busy = false, exhausted = false, pass_done = false, inserting = false;
-    float x = 0.f, y = 0.f, z = 0.f, kth = CUDART_INF_F;
-    QueryCell c = {};
-    int Rin = 1, R = 2, az = 0, ay = 0, nlog = 0;
-    uint32_t j = 0, e = 0, j2 = 0, e2 = 0;
-    int32_t *oi = nullptr; float *od = nullptr;
-    RegList<K> list; list.init();
-    auto kth_of = [&]() { return key_d2((k == K) ? list.key[K - 1] : list.at(k - 1)); };
-    auto visit = [&](uint32_t pos, const float4 &p) {
-        const float d2 = dist2(x, y, z, p.x, p.y, p.z);
-        if (d2 <= kth) {
-            if (inserting) { list.offer(make_key(d2, __float_as_uint(p.w))); kth = kth_of(); }
-            else { if (nlog < kRingLog) slog[nlog * 128] = pos; ++nlog; }
-        }
-    };
-    for (;;) {
-        // ---- settle ----
-        const unsigned waiting = __ballot_sync(full, (busy && pass_done) || (!busy && !exhausted));
-        const unsigned walking = __ballot_sync(full, busy && !pass_done);
-        if (waiting == 0 && walking == 0) break;
-        if (waiting != 0 && (__popc(waiting) >= kSettleBatch || walking == 0)) {
-            if (busy && pass_done) {
-                bool again = false;
-                if (!inserting) {
-                    if (nlog <= kRingLog) {
-                        for (int q = 0; q < nlog; ++q) { const float4 p = __ldg(g.pts + slog[q * 128]); list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); }
-                        kth = kth_of();
-                    } else { inserting = true; again = true; }          // log overflow: same pass again, inserting while walking
+    uint2 *srun = srun_all + threadIdx.x;
+    const unsigned n = *fix.ring_count;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t t = fix.ring_list[i];
+        float x, y, z; int64_t row; bool empty;
+        if (!load_query(g, v, (int64_t)t, x, y, z, row, empty)) continue;
+        int32_t *oi = out_idx + row * k; float *od = out_d2 + row * k;
+        float kth = od[k - 1];                                    // +inf when the block held fewer than k points
+        const QueryCell c = locate(g, x, y, z);
+        const int R = kth == CUDART_INF_F ? kRingMaxR + 1 : next_ring(g, 1, kth);
+        bool defer = R > kRingMaxR;
+        int ncand = 0, nrun = 0, nlog = 0;
+        if (!defer) {
+            // plan: same conservative margins as row_runs; a range is (first cell | (cells - 1) << 28), at most 7 cells long
+            const float tau_u = to_cell_units(g, kth), rad = sqrtf(tau_u) + 2e-3f;
+            const int z0 = max(max(c.cz - R, 0), (int)floorf(c.uz - rad)), z1 = min(min(c.cz + R, g.nz - 1), (int)floorf(c.uz + rad));
+            const int y0 = max(max(c.cy - R, 0), (int)floorf(c.uy - rad)), y1 = min(min(c.cy + R, g.ny - 1), (int)floorf(c.uy + rad));
+            for (int zz = z0; zz <= z1; ++zz) {
+                const float gz = fmaxf(fmaxf((float)zz - c.uz, c.uz - (float)(zz + 1)) - 2e-3f, 0.f);
+                for (int yy = y0; yy <= y1; ++yy) {
+                    const float gy = fmaxf(fmaxf((float)yy - c.uy, c.uy - (float)(yy + 1)) - 2e-3f, 0.f);
+                    const float D = gy * gy + gz * gz;
+                    if (D > tau_u) continue;
+                    const float w = sqrtf(tau_u - D) + 2e-3f;
+                    const int xlo = max(max(c.cx - R, 0), (int)floorf(c.ux - w)), xhi = min(min(c.cx + R, g.nx - 1), (int)floorf(c.ux + w));
+                    const uint32_t base = (uint32_t)(((size_t)zz * g.ny + yy) * g.nx);
+                    const bool shell = max(abs(zz - c.cz), abs(yy - c.cy)) > 1;
+                    // shell row: one range; inner row: the cells left and right of the 3x3x3 block
+                    const int xa1 = xlo, xb1 = shell ? xhi : min(xhi, c.cx - 2);
+                    const int xa2 = max(xlo, c.cx + 2), xb2 = shell ? -1 : xhi;
+                    if (xa1 <= xb1) { if (ncand < kRingLog) slog[ncand * 128] = (base + (uint32_t)xa1) | ((uint32_t)(xb1 - xa1) << 28); ++ncand; }
+                    if (xa2 <= xb2) { if (ncand < kRingLog) slog[ncand * 128] = (base + (uint32_t)xa2) | ((uint32_t)(xb2 - xa2) << 28); ++ncand; }
                 }
-                if (!again) {
-                    const float cov = covered_d2(g, c, R);
-                    if (cov == CUDART_INF_F || kth < cov) { write_row<K>(list.key, k, oi, od, vec4); busy = false; }
-                    else { Rin = R; R = next_ring(g, R, kth); inserting = kth == CUDART_INF_F; }
-                }
-                az = ay = 0; nlog = 0; pass_done = false; j = e = j2 = e2 = 0;
             }
-            const bool want = !busy && !exhausted;
-            const unsigned takers = __ballot_sync(full, want);
-            if (takers) {
-                unsigned base = 0;
-                if (lane == __ffs(takers) - 1) base = atomicAdd(fix.ring_cursor, (unsigned)__popc(takers));
-                base = __shfl_sync(full, base, __ffs(takers) - 1);
-                if (want) {
-                    const unsigned i = base + __popc(takers & ((1u << lane) - 1));
-                    int64_t row; bool empty;
-                    if (i >= n) exhausted = true;
-                    else if (load_query(g, v, (int64_t)fix.ring_list[i], x, y, z, row, empty)) {
-                        oi = out_idx + row * k; od = out_d2 + row * k;
-                        if (vec4 && K >= 4 && k == K) {
+            defer = ncand > kRingLog;
+        }
+        if (!defer) {
+            // probe: four ranges per step, bitmap words first, tests after
+            for (int r0 = 0; r0 < ncand; r0 += 4) {
+                uint32_t cw[4], w0[4], w1[4];
 #pragma unroll
-                            for (int t = 0; t + 3 < K; t += 4) {
-                                const int4 a = reinterpret_cast<const int4 *>(oi)[t >> 2]; const float4 d = reinterpret_cast<const float4 *>(od)[t >> 2];
-                                list.key[t] = a.x < 0 ? PCC_EMPTY_KEY : make_key(d.x, (uint32_t)a.x); list.key[t + 1] = a.y < 0 ? PCC_EMPTY_KEY : make_key(d.y, (uint32_t)a.y);
-                                list.key[t + 2] = a.z < 0 ? PCC_EMPTY_KEY : make_key(d.z, (uint32_t)a.z); list.key[t + 3] = a.w < 0 ? PCC_EMPTY_KEY : make_key(d.w, (uint32_t)a.w);
-                            }
-                        } else {
+                for (int u = 0; u < 4; ++u) {
+                    cw[u] = slog[min(r0 + u, ncand - 1) * 128];
+                    const uint32_t b = cw[u] & 0x0fffffffu;
+                    w0[u] = __ldg(g.occ + (b >> 5)); w1[u] = __ldg(g.occ + (b >> 5) + 1);
+                }
 #pragma unroll
-                            for (int t = 0; t < K; ++t) { list.key[t] = PCC_EMPTY_KEY; if (t < k) { const int32_t a = oi[t]; if (a >= 0) list.key[t] = make_key(od[t], (uint32_t)a); } }
-                        }
-                        c = locate(g, x, y, z);
-                        kth = kth_of();
-                        Rin = 1; R = next_ring(g, 1, kth); inserting = kth == CUDART_INF_F;
-                        az = ay = 0; nlog = 0; pass_done = false; j = e = j2 = e2 = 0;
-                        busy = true;
-                    }
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t b = cw[u] & 0x0fffffffu, len = (cw[u] >> 28) + 1u;
+                    const uint32_t bits = __funnelshift_r(w0[u], w1[u], b & 31u) & ((1u << len) - 1u);
+                    if (r0 + u < ncand && bits != 0u) { if (nrun < kRingRuns) srun[nrun * 128] = make_uint2(b, b + len); ++nrun; }
                 }
             }
+            defer = nrun > kRingRuns;
         }
-        // ---- advance: next run of this lane's pass ----
-        if (busy && !pass_done && j >= e) {
-            if (j2 < e2) { j = j2; e = e2; j2 = e2 = 0; }
-            else {
-                const int n1 = 2 * R + 1;
-                const float tau_u = to_cell_units(g, kth);
-#pragma unroll 1
-                for (int t = 0; t < kRowsPerStep; ++t) {
-                    if (az == n1) { pass_done = true; break; }
-                    const RowRuns r = row_runs(g, c, Rin, R, tau_u, az, ay);
-                    if (++ay == n1) { ay = 0; ++az; }
-                    if (r.j1 < r.e1) { j = r.j1; e = r.e1; j2 = r.j2; e2 = r.e2; break; }
-                    if (r.j2 < r.e2) { j = r.j2; e = r.e2; break; }
-                }
+        if (!defer && nrun > 0) {
+            // bounds: cell ranges -> point ranges
+            for (int r0 = 0; r0 < nrun; r0 += 4) {
+                uint2 pr[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const uint2 cr = srun[min(r0 + u, nrun - 1) * 128]; pr[u] = make_uint2(__ldg(g.cell_start + cr.x), __ldg(g.cell_start + cr.y)); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (r0 + u < nrun) srun[(r0 + u) * 128] = pr[u];
             }
+            // walk: four points per step, taken across run boundaries (every run is non-empty: the bitmap is exact)
+            int r = 0;
+            uint2 cur = srun[0];
+            bool more = true;
+            while (more) {
+                uint32_t pos[4]; bool ok[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (cur.x >= cur.y && r + 1 < nrun) { ++r; cur = srun[r * 128]; }
+                    ok[u] = cur.x < cur.y; pos[u] = ok[u] ? cur.x : 0u;
+                    if (ok[u]) ++cur.x;
+                }
+                more = cur.x < cur.y || r + 1 < nrun;
+                float4 p[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) p[u] = __ldg(g.pts + pos[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (ok[u] && dist2(x, y, z, p[u].x, p[u].y, p[u].z) <= kth) { if (nlog < kRingLog) slog[nlog * 128] = pos[u]; ++nlog; }
+            }
+            defer = nlog > kRingLog;
         }
-        // ---- walk: up to four points of the run in hand ----
-        if (busy && j < e) {
-            const uint32_t last = e - 1;
-            const float4 p0 = __ldg(g.pts + j), p1 = __ldg(g.pts + min(j + 1, last)), p2 = __ldg(g.pts + min(j + 2, last)), p3 = __ldg(g.pts + min(j + 3, last));
-            visit(j, p0);
-            if (j + 1 < e) visit(j + 1, p1);
-            if (j + 2 < e) visit(j + 2, p2);
-            if (j + 3 < e) visit(j + 3, p3);
-            j += 4;
+        RegList<K> list;
+        if (!defer && nlog > 0) {
+            if (vec4 && K >= 4 && k == K) {
+#pragma unroll
+                for (int j = 0; j + 3 < K; j += 4) {
+                    const int4 a = reinterpret_cast<const int4 *>(oi)[j >> 2]; const float4 d = reinterpret_cast<const float4 *>(od)[j >> 2];
+                    list.key[j] = a.x < 0 ? PCC_EMPTY_KEY : make_key(d.x, (uint32_t)a.x); list.key[j + 1] = a.y < 0 ? PCC_EMPTY_KEY : make_key(d.y, (uint32_t)a.y);
+                    list.key[j + 2] = a.z < 0 ? PCC_EMPTY_KEY : make_key(d.z, (uint32_t)a.z); list.key[j + 3] = a.w < 0 ? PCC_EMPTY_KEY : make_key(d.w, (uint32_t)a.w);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < K; ++j) { list.key[j] = PCC_EMPTY_KEY; if (j < k) { const int32_t a = oi[j]; if (a >= 0) list.key[j] = make_key(od[j], (uint32_t)a); } }
+            }
+            for (int q = 0; q < nlog; ++q) { const float4 p = __ldg(g.pts + slog[q * 128]); list.offer(make_key(dist2(x, y, z, p.x, p.y, p.z), __float_as_uint(p.w))); }
+            kth = key_d2((k == K) ? list.key[K - 1] : list.at(k - 1));
         }
+        if (!defer) {
+            const float cov = covered_d2(g, c, R);
+            defer = !(cov == CUDART_INF_F || kth < cov);
+        }
+        if (defer) push_list(fix.wide_list, fix.wide_count, t);
+        else if (nlog > 0) write_row<K>(list.key, k, oi, od, vec4);
     }
 }
 
@@ -705,6 +849,7 @@ static void launch_knn_reg(const Grid &g, const QueryView &v, int k, int32_t *oi
 }
 template <int K>
 static void launch_knn_cell(const Grid &g, const QueryView &v, int k, int32_t *oi, float *od, int vec4, FixList fix, cudaStream_t s) {
+    fix.wide_list = nullptr;            // this variant grows its rings in the kernel; every listed query goes to knn_fixup_kernel
     cudaMemsetAsync(fix.count, 0, sizeof(unsigned), s);
     knn_cell_kernel<K><<<nblocks(v.nq, kCellWarps * 32), kCellWarps * 32, 0, s>>>(g, v, k, oi, od, vec4, fix);
     PCC_LAUNCHED();
@@ -717,12 +862,14 @@ static int launch_knn_fast(pcc_index *idx, const Grid &g, const QueryView &v, in
     cub::DeviceSelect::Flagged(nullptr, tmp, cub::CountingInputIterator<uint32_t>(0), fix.ring_flag, fix.ring_list, fix.ring_count, (int)v.nq, s);
     PCC_TRY(idx->cub_tmp.reserve(tmp));
     cudaMemsetAsync(fix.count, 0, sizeof(unsigned), s);
-    cudaMemsetAsync(fix.ring_cursor, 0, sizeof(unsigned), s);
+    cudaMemsetAsync(fix.wide_count, 0, sizeof(unsigned), s);
     knn_fast_kernel<K><<<nblocks(v.nq, FastCfg<K>::threads), FastCfg<K>::threads, 0, s>>>(g, v, k, oi, od, vec4, fix);
     PCC_LAUNCHED();
     PCC_CUDA(cub::DeviceSelect::Flagged(idx->cub_tmp.p, tmp, cub::CountingInputIterator<uint32_t>(0), fix.ring_flag, fix.ring_list, fix.ring_count, (int)v.nq, s));
     PCC_LAUNCHED();
-    knn_rings_kernel<K><<<148 * (K <= 16 ? PCC_RINGS_MB : 3), 128, 0, s>>>(g, v, k, oi, od, vec4, fix);
+    knn_rings_kernel<K><<<148 * 16, 128, 0, s>>>(g, v, k, oi, od, vec4, fix);
+    PCC_LAUNCHED();
+    knn_wide_kernel<<<148 * 8, 128, 0, s>>>(g, v, k, oi, od, fix);
     PCC_LAUNCHED();
     knn_fixup_kernel<K><<<148 * 4, 128, 0, s>>>(g, v, k, oi, od, vec4, fix);
     PCC_LAUNCHED();
@@ -733,10 +880,11 @@ static int launch_knn_fast(pcc_index *idx, const Grid &g, const QueryView &v, in
 
 using namespace pcc;
 
-static int check_common(pcc_index *idx) {
+static int check_common(pcc_index *idx, void *stream) {
     if (!idx) return fail(PCC_ERR_INVALID, "idx is NULL");
     if (!idx->built) return fail(PCC_ERR_STATE, "index not built (call pcc_build first)");
     PCC_CUDA(cudaSetDevice(idx->device));
+    if (!idx->occ_valid) PCC_TRY(rebuild_occupancy(idx, (cudaStream_t)stream));     // first query after pcc_adopt
     return PCC_OK;
 }
 
@@ -773,11 +921,11 @@ static int knn_impl(pcc_index *idx, const void *q, int64_t nq, int stride_bytes,
         // per-thread walk even at 80 queries per cell (profiles/r1/cell_kernel_probe.jsonl), so it is never chosen automatically.
         const char *cell_env = getenv("PCC_CELL_KERNEL");
         const bool use_cell = cell_env && atoi(cell_env) != 0;
-        FixList fix{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        FixList fix{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
         if (k > 1 && k <= 32 && !exact_only) {
-            PCC_TRY(idx->misc.reserve((size_t)v.nq * 9 + 256));
-            fix.count = idx->misc.as<unsigned>(); fix.ring_count = fix.count + 1; fix.ring_cursor = fix.count + 30;
-            fix.list = idx->misc.as<uint32_t>() + 32; fix.ring_list = fix.list + v.nq; fix.ring_flag = (uint8_t *)(fix.ring_list + v.nq);
+            PCC_TRY(idx->misc.reserve((size_t)v.nq * 13 + 256));
+            fix.count = idx->misc.as<unsigned>(); fix.ring_count = fix.count + 1; fix.wide_count = fix.count + 30;
+            fix.list = idx->misc.as<uint32_t>() + 32; fix.ring_list = fix.list + v.nq; fix.wide_list = fix.ring_list + v.nq; fix.ring_flag = (uint8_t *)(fix.wide_list + v.nq);
             if (want_stats) { fix.stats = (unsigned long long *)(idx->misc.as<uint32_t>() + 2); PCC_CUDA(cudaMemsetAsync(fix.stats, 0, 112, s)); }
         }
         if (k == 1) launch_knn_reg<1>(g, v, k, oi, od, vec4, s);
@@ -808,6 +956,7 @@ static int knn_impl(pcc_index *idx, const void *q, int64_t nq, int stride_bytes,
         const double q = (double)std::max<unsigned long long>(h[0], 1);
         fprintf(stderr, "[pcc stats] queries=%llu logged/q=%.1f log_overflow=%.5f need_ring2=%.3f fixup=%.5f members/q=%.2f\n",
                 h[0], h[1] / q, h[3] / q, h[4] / q, h[5] / q, h[6] / q);
+        fprintf(stderr, "[pcc stats] wide queries=%llu steps/q=%.1f final R: <=1 %llu, 2 %llu, 3 %llu, 4-7 %llu, 8-15 %llu, 16+ %llu\n", h[2], h[7] / (double)std::max<unsigned long long>(h[2], 1), h[8], h[9], h[10], h[11], h[12], h[13]);
     }
     if (mem == PCC_HOST) {
         PCC_TRY(copy_out(out_idx, oi, cells * 4, mem, s));
@@ -820,7 +969,7 @@ static int knn_impl(pcc_index *idx, const void *q, int64_t nq, int stride_bytes,
 extern "C" {
 
 int pcc_knn(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int k, int32_t *out_idx, float *out_d2, int *k_eff, int mem, void *stream) {
-    PCC_TRY(check_common(idx));
+    PCC_TRY(check_common(idx, stream));
     if (k < 1 || k > PCC_MAX_K) return fail(PCC_ERR_INVALID, "k=%d outside 1..%d", k, PCC_MAX_K);
     cudaStream_t s = (cudaStream_t)stream;
     // Large host batches: two-slot pipeline, 1 Mi queries per chunk (16 MB in, k x 8 MB out), so the device->host copy of
@@ -852,7 +1001,7 @@ int pcc_knn(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int k, 
 }
 
 int pcc_knn_mean_dist(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int mean_k, float *out_mean, int mem, void *stream) {
-    PCC_TRY(check_common(idx));
+    PCC_TRY(check_common(idx, stream));
     if (mean_k < 1 || mean_k + 1 > PCC_MAX_K) return fail(PCC_ERR_INVALID, "mean_k=%d outside 1..%d", mean_k, PCC_MAX_K - 1);
     cudaStream_t s = (cudaStream_t)stream;
     Queries qs;
@@ -892,7 +1041,7 @@ int pcc_knn_mean_dist(pcc_index *idx, const void *q, int64_t nq, int stride_byte
 }
 
 int pcc_normals_knn(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int k, const float viewpoint[3], float *out, int mem, void *stream) {
-    PCC_TRY(check_common(idx));
+    PCC_TRY(check_common(idx, stream));
     if (k < 1 || k > PCC_MAX_K) return fail(PCC_ERR_INVALID, "k=%d outside 1..%d", k, PCC_MAX_K);
     cudaStream_t s = (cudaStream_t)stream;
     Queries qs;
@@ -929,7 +1078,7 @@ int pcc_normals_knn(pcc_index *idx, const void *q, int64_t nq, int stride_bytes,
 // src working copy lives in idx->stage4-independent buffer `parent` is reserved for clustering; ICP uses qbuf-sized `keys64b`
 int pcc_icp_step(pcc_index *idx, void *src_inout, int64_t ns, int stride_bytes, const float *T_apply, double sums[16], int64_t *count,
                  int32_t *corr_idx, float *corr_d2, int mem, void *stream) {
-    PCC_TRY(check_common(idx));
+    PCC_TRY(check_common(idx, stream));
     if (ns < 0 || stride_bytes < 12 || (stride_bytes & 3)) return fail(PCC_ERR_INVALID, "bad source cloud (ns=%lld stride=%d)", (long long)ns, stride_bytes);
     if (!sums || !count) return fail(PCC_ERR_INVALID, "sums / count are NULL");
     cudaStream_t s = (cudaStream_t)stream;

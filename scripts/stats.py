@@ -12,6 +12,7 @@ q = synth.sweep_queries(ref, n, 5002, 0.01, stride4=True)
 dref, dq = torch.from_numpy(ref).cuda(), torch.from_numpy(q).cuda()
 for occ in [float(v) for v in sys.argv[3].split(",")]:
     os.environ["PCC_OCC"] = str(occ)
-    s = GridSearch(0).setInputCloud(dref, k_hint=16); s.setTiming(True)
-    s.nearestKSearch(dq, 16); s.nearestKSearch(dq, 16)
+    k = int(sys.argv[4]) if len(sys.argv) > 4 else 16
+    s = GridSearch(0).setInputCloud(dref, k_hint=k); s.setTiming(True)
+    s.nearestKSearch(dq, k); s.nearestKSearch(dq, k)
     print("occ", occ, s.grid_info(), "ms", s.lastKernelMs(), flush=True)

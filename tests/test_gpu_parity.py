@@ -463,3 +463,67 @@ def test_descriptor_nn_vs_oracle(GS):
         assert np.array_equal(di.cpu().numpy(), oi) and np.array_equal(bits(dd.cpu().numpy()), bits(od))
         corr = match_rift_features_knn(ref, qry)
         assert corr == [0] + oi[(oi >= 0) & (od < np.float32(0.05))].tolist()
+
+
+# ---------------------------------------------------------------- the passes behind the 3x3x3 block (rings / wide / tied)
+@pytest.mark.parametrize("k", [2, 5, 8, 16, 31, 32])
+def test_knn_density_gradient_rings_and_wide_passes(GS, k):
+    """A dense core with a halo 30x and 1000x sparser: core queries settle in the 3x3x3 block, halo queries need one or two
+    more rings (knn_rings_kernel), and queries out in the thin halo or beyond it see fewer than k points in their block
+    (knn_wide_kernel, one warp per query, rings until covered)."""
+    rng = np.random.default_rng(100 + k)
+    ref = np.concatenate([rng.normal(0, 0.2, (60000, 3)), rng.normal(0, 0.8, (8000, 3)), rng.uniform(-6, 6, (1500, 3))]).astype(np.float32)
+    qry = np.concatenate([ref[::7] + rng.normal(0, 0.01, (len(ref[::7]), 3)), rng.uniform(-7, 7, (3000, 3)), rng.uniform(-40, 40, (200, 3))]).astype(np.float32)
+    s = GS().setInputCloud(ref, k_hint=k)
+    gi, gd, _ = s.nearestKSearch(qry, k)
+    oi, od, _ = oracle.KdTree(ref).knn(qry, k)
+    assert_knn_equal(gi, gd, oi, od)
+
+
+def test_knn_few_and_many_tied_queries(GS):
+    """More than K candidates tied at the k-th distance: a short list of such queries is finished by the warp-per-query
+    kernel, a long one (> 4096) by the per-thread exact kernel; both must give the canonical (d2, index) order."""
+    rng = np.random.default_rng(5)
+    g = np.arange(6, dtype=np.float32) * 0.125
+    patch = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3) + np.float32(8.0)             # 216 lattice points, exact in fp32
+    ref = np.concatenate([rng.uniform(0, 4, (30000, 3)).astype(np.float32), patch])
+    ref = ref[rng.permutation(len(ref))]
+    s = GS().setInputCloud(ref, cell_hint=0.3)
+    tree = oracle.KdTree(ref)
+    for k in (4, 7, 16):
+        gi, gd, _ = s.nearestKSearch(ref, k)                                                              # 216 tied queries
+        oi, od, _ = tree.knn(ref, k)
+        assert_knn_equal(gi, gd, oi, od)
+    g = np.arange(20, dtype=np.float32) * 0.25
+    lattice = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)                            # 8000 tied queries
+    lattice = lattice[rng.permutation(len(lattice))]
+    s = GS().setInputCloud(lattice)
+    for k in (7, 16):
+        gi, gd, _ = s.nearestKSearch(lattice, k)
+        oi, od, _ = oracle.KdTree(lattice).knn(lattice, k)
+        assert_knn_equal(gi, gd, oi, od)
+
+
+def test_knn_adopted_grid_rebuilds_occupancy(GS):
+    """pcc_export / pcc_adopt (the multi-GPU broadcast path): the adopting index derives its occupancy bitmap on the first query."""
+    import torch
+    ref = synth.room(50000, 12)
+    qry = np.concatenate([ref[::5] + np.float32(0.004), np.random.default_rng(2).uniform(-1, 6, (2000, 3)).astype(np.float32)])
+    a = GS().setInputCloud(torch.from_numpy(ref).cuda(), k_hint=8)
+    meta, a_pts, a_cells = a.export()
+    b = GS()
+    _, b_pts, b_cells = b.adopt(meta)
+
+    def view(ptr, nbytes):
+        class _Mem:
+            pass
+        m = _Mem()
+        m.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+        return torch.as_tensor(m, device="cuda:0")
+
+    view(b_pts, int(meta[0]) * 16).copy_(view(a_pts, int(meta[0]) * 16))
+    view(b_cells, (int(meta[11]) + 1) * 4).copy_(view(a_cells, (int(meta[11]) + 1) * 4))
+    torch.cuda.synchronize()
+    gi, gd, _ = b.nearestKSearch(qry, 8)
+    oi, od, _ = oracle.KdTree(ref).knn(qry, 8)
+    assert_knn_equal(gi, gd, oi, od)
