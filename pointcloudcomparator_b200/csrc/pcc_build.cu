@@ -247,6 +247,9 @@ void pcc_destroy(pcc_index *idx) {
                    &idx->cub_tmp, &idx->out_i, &idx->out_f, &idx->out_l, &idx->keys64, &idx->keys64b, &idx->misc, &idx->parent, &idx->inv_pos};
     for (Buf *b : bufs) b->release();
     if (idx->h_pinned) cudaFreeHost(idx->h_pinned);
+    if (idx->aux_stream) cudaStreamDestroy(idx->aux_stream);
+    if (idx->ev_fork) cudaEventDestroy(idx->ev_fork);
+    if (idx->ev_join) cudaEventDestroy(idx->ev_join);
     if (idx->ev0) cudaEventDestroy(idx->ev0);
     if (idx->ev1) cudaEventDestroy(idx->ev1);
     delete idx;

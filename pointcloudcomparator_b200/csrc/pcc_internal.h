@@ -78,6 +78,9 @@ struct pcc_index {
     pcc_index *shadow = nullptr;
     const pcc_index *grid_owner = nullptr;
     cudaStream_t pipe_stream[2] = {nullptr, nullptr};
+    // the wide pass of pcc_knn runs beside the ring pass on this stream (both are latency-bound and touch different rows)
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     pcc::Grid grid() const {
         const pcc_index *o = grid_owner ? grid_owner : this;

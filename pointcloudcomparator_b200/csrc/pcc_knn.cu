@@ -81,7 +81,7 @@ constexpr unsigned kTiedToWide = 4096;   // a tied-query list this short is fini
 // queries the fast path could not prove exact (listed by knn_fast_kernel)
 // `ring_flag[t]` = 1 for the queries whose 3x3x3 block did not prove the k-th distance; a stream compaction turns the flags
 // into `ring_list` / `ring_count` IN PROCESSING ORDER (neighbouring lanes stay neighbours in space) for knn_rings_kernel.
-struct FixList { uint32_t *list; unsigned *count; unsigned long long *stats; uint32_t *ring_list; unsigned *ring_count; uint8_t *ring_flag; uint32_t *wide_list; unsigned *wide_count; };   // stats: optional debug counters (PCC_STATS=1)
+struct FixList { uint32_t *list; unsigned *count; unsigned long long *stats; uint32_t *ring_list; unsigned *ring_count; uint8_t *ring_flag; uint32_t *wide_list; unsigned *wide_count; uint32_t *late_list; unsigned *late_count; };   // stats: optional debug counters (PCC_STATS=1)
 // append `value` to a device list, one atomic per warp
 __device__ __forceinline__ void push_list(uint32_t *list, unsigned *count, uint32_t value) {
     const unsigned mask = __activemask();
@@ -205,36 +205,34 @@ __global__ void __launch_bounds__(FastCfg<K>::threads, FastCfg<K>::min_blocks) k
 // hundreds of rows long (measured: 35 k such queries cost 0.9 ms).  Here ONE WARP owns a query.  A pass takes its rows 32
 // at a time: each lane plans one row (run bounds), the occupied runs are appended to a run list with their length prefix
 // sums, and the points of all listed runs are then dealt round-robin to the lanes (point q -> lane q % 32), so every lane
-// is busy whatever the run lengths.  Points inside the current ball are appended (ballot + prefix count) to a per-warp
-// buffer of 64-bit (d2, index) keys in shared memory; when the buffer fills up the k smallest keys are extracted by
-// repeated warp-wide minimum, which also tightens the ball.  Passes grow ring by ring exactly like the per-thread search
-// (covered_d2 / next_ring), so the result is exact for any density.
-constexpr int kWideCap = 128;                    // keys per warp buffer (4 per lane)
-__device__ __forceinline__ nkey_t warp_min_key(nkey_t v) {
+// is busy whatever the run lengths.  The best keys so far live one per lane, sorted (lane j = j-th smallest 64-bit
+// (d2, index) key); a step whose points reach inside the current ball sorts them across the warp and merges them in
+// with a bitonic network of shuffles (about 200 instructions), which also tightens the ball.  Passes grow ring by ring
+// exactly like the per-thread search (covered_d2 / next_ring), so the result is exact for any density.
+// warp-wide bitonic network over one 64-bit key per lane (ascending by lane)
+__device__ __forceinline__ nkey_t warp_sort_keys(nkey_t v, int lane) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const nkey_t w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; }
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int j = size >> 1; j > 0; j >>= 1) {
+            const nkey_t o = __shfl_xor_sync(0xffffffffu, v, j);
+            const bool keep_min = ((lane & j) == 0) == ((lane & size) == 0);
+            v = (keep_min == (o < v)) ? o : v;
+        }
+    }
     return v;
 }
-// k smallest of buf[0, cnt) -> buf[0, min(cnt, k)) ascending; returns the new count
-__device__ __forceinline__ int wide_truncate(nkey_t *buf, int cnt, int k, int lane) {
-    nkey_t v[kWideCap / 32];
+// best (ascending by lane) and batch (any order) -> the 32 smallest of both, ascending by lane
+__device__ __forceinline__ nkey_t warp_merge_keys(nkey_t best, nkey_t batch, int lane) {
+    batch = warp_sort_keys(batch, lane);
+    const nkey_t r = __shfl_sync(0xffffffffu, batch, 31 - lane);
+    nkey_t v = r < best ? r : best;                      // bitonic sequence holding the 32 smallest
 #pragma unroll
-    for (int i = 0; i < kWideCap / 32; ++i) v[i] = (lane + 32 * i) < cnt ? buf[lane + 32 * i] : PCC_EMPTY_KEY;
-    __syncwarp();
-    const int keep = min(cnt, k);
-    nkey_t mine = PCC_EMPTY_KEY;
-    for (int it = 0; it < keep; ++it) {
-        nkey_t m = v[0];
-#pragma unroll
-        for (int i = 1; i < kWideCap / 32; ++i) m = v[i] < m ? v[i] : m;
-        const nkey_t best = warp_min_key(m);
-#pragma unroll
-        for (int i = 0; i < kWideCap / 32; ++i) if (v[i] == best) v[i] = PCC_EMPTY_KEY;      // keys are unique (one per point)
-        if (lane == it) mine = best;
+    for (int j = 16; j > 0; j >>= 1) {
+        const nkey_t o = __shfl_xor_sync(0xffffffffu, v, j);
+        v = (((lane & j) == 0) == (o < v)) ? o : v;
     }
-    if (lane < keep) buf[lane] = mine;
-    __syncwarp();
-    return keep;
+    return v;
 }
 constexpr int kWideRuns = 64;                    // runs planned per chunk of 32 rows (two strips per row at most)
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
@@ -242,30 +240,35 @@ __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
     for (int o = 1; o < 32; o <<= 1) { const uint32_t w = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += w; }
     return v;
 }
-__global__ void __launch_bounds__(128, 4) knn_wide_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, FixList fix) {
-    __shared__ nkey_t sbuf[4 * kWideCap];
+__global__ void __launch_bounds__(128, 5) knn_wide_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, FixList fix,
+                                                         const uint32_t *__restrict__ wlist, const unsigned *__restrict__ wcount, int take_tied) {
     __shared__ uint32_t srun_j[4 * kWideRuns], srun_len[4 * kWideRuns], srun_off[4 * (kWideRuns + 1)];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    nkey_t *buf = sbuf + wib * kWideCap;
     uint32_t *run_j = srun_j + wib * kWideRuns, *run_len = srun_len + wib * kWideRuns, *run_off = srun_off + wib * (kWideRuns + 1);
     // a SHORT list of tied queries (more than K candidates at the k-th distance) is taken along: as a handful of single
     // threads in knn_fixup_kernel they are a 0.1 ms latency tail; a long one (lattice data) stays with that kernel
-    const unsigned n_wide = *fix.wide_count, n_tied = *fix.count <= kTiedToWide ? *fix.count : 0u, n = n_wide + n_tied;
+    const unsigned n_wide = *wcount, n_tied = (take_tied && *fix.count <= kTiedToWide) ? *fix.count : 0u, n = n_wide + n_tied;
     const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
     for (unsigned i = blockIdx.x * 4 + wib; i < n; i += gridDim.x * 4) {
         float x, y, z; int64_t row; bool empty;
-        if (!load_query(g, v, (int64_t)(i < n_wide ? fix.wide_list[i] : fix.list[i - n_wide]), x, y, z, row, empty)) continue;      // warp-uniform
+        if (!load_query(g, v, (int64_t)(i < n_wide ? wlist[i] : fix.list[i - n_wide]), x, y, z, row, empty)) continue;      // warp-uniform
         const QueryCell c = locate(g, x, y, z);
-        int cnt = 0, Rin = -1, R = 3;            // a listed query is known not to be settled by the 3x3x3 block
-        float tau = CUDART_INF_F;
+        int Rin = -1, R = 3;                     // a listed query is known not to be settled by the 3x3x3 block
+        nkey_t best = PCC_EMPTY_KEY;             // lane j: the j-th smallest (d2, index) key seen so far
+        float tau = CUDART_INF_F;                // d2 of the k-th of them: later points must beat or tie it
         unsigned long long steps = 0;
         for (;;) {
             const int n1 = 2 * R + 1, nrows = n1 * n1;
             const float tau_u = to_cell_units(g, tau);
-            for (int row0 = 0; row0 < nrows; row0 += 32) {
-                // plan: one row per lane -> occupied runs, appended to the warp's run list
+            const int per = Rin < 0 ? 2 : 1;     // a whole-block pass has one run per row: plan two rows per lane
+            for (int row0 = 0; row0 < nrows; row0 += 32 * per) {
+                // plan: rows -> occupied runs, appended to the warp's run list (at most two per lane)
                 RowRuns r; r.j1 = r.e1 = r.j2 = r.e2 = 0;
                 if (row0 + lane < nrows) r = row_runs(g, c, Rin, R, tau_u, (row0 + lane) / n1, (row0 + lane) % n1);
+                if (per == 2 && row0 + 32 + lane < nrows) {
+                    const RowRuns r2 = row_runs(g, c, Rin, R, tau_u, (row0 + 32 + lane) / n1, (row0 + 32 + lane) % n1);
+                    r.j2 = r2.j1; r.e2 = r2.e1;
+                }
                 const unsigned m1 = __ballot_sync(full, r.j1 < r.e1), m2 = __ballot_sync(full, r.j2 < r.e2);
                 const int nrun = __popc(m1) + __popc(m2);
                 if (nrun == 0) continue;
@@ -278,43 +281,35 @@ __global__ void __launch_bounds__(128, 4) knn_wide_kernel(Grid g, QueryView v, i
                 run_off[lane] = ia - la; run_off[lane + 32] = ta + ib - lb;
                 if (lane == 0) run_off[kWideRuns] = P;
                 __syncwarp();
-                // flat walk: point q of the concatenated runs belongs to lane q % 32 -- every lane busy whatever the run lengths
+                // flat walk: point q of the concatenated runs belongs to lane q % 32 -- every lane busy whatever the run
+                // lengths; two points per lane and step so two loads are in flight
                 int rc = 0;
-                for (uint32_t q0 = 0; q0 < P; q0 += 32) {
-                    const uint32_t q = q0 + lane;
-                    bool has = false; nkey_t key = PCC_EMPTY_KEY;
-                    if (q < P) {
-                        while (q >= run_off[rc + 1]) ++rc;
-                        const float4 p = __ldg(g.pts + run_j[rc] + (q - run_off[rc]));
-                        const float d2 = dist2(x, y, z, p.x, p.y, p.z);
-                        has = d2 <= tau; key = make_key(d2, __float_as_uint(p.w));
+                for (uint32_t q0 = 0; q0 < P; q0 += 64) {
+                    bool has[2] = {false, false}; nkey_t key[2] = {PCC_EMPTY_KEY, PCC_EMPTY_KEY}; float4 p[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const uint32_t q = q0 + 32 * u + lane;
+                        has[u] = q < P;
+                        if (has[u]) { while (q >= run_off[rc + 1]) ++rc; p[u] = __ldg(g.pts + run_j[rc] + (q - run_off[rc])); }
                     }
-                    const unsigned hit = __ballot_sync(full, has);
-                    if (hit) {
-                        if (has) buf[cnt + __popc(hit & lt)] = key;
-                        cnt += __popc(hit);
-                        __syncwarp();
-                        if (cnt > kWideCap - 32) {
-                            cnt = wide_truncate(buf, cnt, k, lane);
-                            if (cnt == k) tau = key_d2(buf[k - 1]);        // later points must beat (or tie) the k-th key
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if (has[u]) { const float d2 = dist2(x, y, z, p[u].x, p[u].y, p[u].z); has[u] = d2 <= tau; key[u] = has[u] ? make_key(d2, __float_as_uint(p[u].w)) : PCC_EMPTY_KEY; }
+                        if (__ballot_sync(full, has[u])) {
+                            best = warp_merge_keys(best, key[u], lane);
+                            tau = key_d2(__shfl_sync(full, best, k - 1));
                         }
                     }
                     ++steps;
                 }
                 __syncwarp();
             }
-            cnt = wide_truncate(buf, cnt, k, lane);
-            const float kth = cnt == k ? key_d2(buf[k - 1]) : CUDART_INF_F;
-            tau = kth;
             const float cov = covered_d2(g, c, R);
-            if (cov == CUDART_INF_F || kth < cov) break;
-            Rin = R; R = next_ring(g, R, kth);
+            if (cov == CUDART_INF_F || tau < cov) break;
+            Rin = R; R = next_ring(g, R, tau);
         }
         if (fix.stats && lane == 0) { atomicAdd(fix.stats + 2, 1ull); atomicAdd(fix.stats + 7, steps); atomicAdd(fix.stats + 8 + (R <= 1 ? 0 : R == 2 ? 1 : R == 3 ? 2 : R < 8 ? 3 : R < 16 ? 4 : 5), 1ull); }
-        if (lane < k) {
-            const nkey_t key = lane < cnt ? buf[lane] : PCC_EMPTY_KEY;
-            out_idx[row * k + lane] = key_idx(key); out_d2[row * k + lane] = key_d2(key);
-        }
+        if (lane < k) { out_idx[row * k + lane] = key_idx(best); out_d2[row * k + lane] = key_d2(best); }
         __syncwarp();
     }
 }
@@ -447,7 +442,7 @@ __global__ void __launch_bounds__(128, K <= 16 ? PCC_RINGS_MB : 4) knn_rings_ker
             const float cov = covered_d2(g, c, R);
             defer = !(cov == CUDART_INF_F || kth < cov);
         }
-        if (defer) push_list(fix.wide_list, fix.wide_count, t);
+        if (defer) push_list(fix.late_list, fix.late_count, t);
         else if (nlog > 0) write_row<K>(list.key, k, oi, od, vec4);
     }
 }
@@ -861,15 +856,27 @@ static int launch_knn_fast(pcc_index *idx, const Grid &g, const QueryView &v, in
     size_t tmp = 0;
     cub::DeviceSelect::Flagged(nullptr, tmp, cub::CountingInputIterator<uint32_t>(0), fix.ring_flag, fix.ring_list, fix.ring_count, (int)v.nq, s);
     PCC_TRY(idx->cub_tmp.reserve(tmp));
+    if (!idx->aux_stream) {
+        PCC_CUDA(cudaStreamCreateWithFlags(&idx->aux_stream, cudaStreamNonBlocking));
+        PCC_CUDA(cudaEventCreateWithFlags(&idx->ev_fork, cudaEventDisableTiming));
+        PCC_CUDA(cudaEventCreateWithFlags(&idx->ev_join, cudaEventDisableTiming));
+    }
     cudaMemsetAsync(fix.count, 0, sizeof(unsigned), s);
-    cudaMemsetAsync(fix.wide_count, 0, sizeof(unsigned), s);
+    cudaMemsetAsync(fix.wide_count, 0, 2 * sizeof(unsigned), s);          // wide_count and late_count are adjacent
     knn_fast_kernel<K><<<nblocks(v.nq, FastCfg<K>::threads), FastCfg<K>::threads, 0, s>>>(g, v, k, oi, od, vec4, fix);
     PCC_LAUNCHED();
+    // fork: the wide queries (and a short tied list) on the aux stream, beside the compaction + ring pass on `s`
+    PCC_CUDA(cudaEventRecord(idx->ev_fork, s));
+    PCC_CUDA(cudaStreamWaitEvent(idx->aux_stream, idx->ev_fork, 0));
+    knn_wide_kernel<<<148 * 6, 128, 0, idx->aux_stream>>>(g, v, k, oi, od, fix, fix.wide_list, fix.wide_count, 1);
+    PCC_LAUNCHED();
+    PCC_CUDA(cudaEventRecord(idx->ev_join, idx->aux_stream));
     PCC_CUDA(cub::DeviceSelect::Flagged(idx->cub_tmp.p, tmp, cub::CountingInputIterator<uint32_t>(0), fix.ring_flag, fix.ring_list, fix.ring_count, (int)v.nq, s));
     PCC_LAUNCHED();
     knn_rings_kernel<K><<<148 * 16, 128, 0, s>>>(g, v, k, oi, od, vec4, fix);
     PCC_LAUNCHED();
-    knn_wide_kernel<<<148 * 8, 128, 0, s>>>(g, v, k, oi, od, fix);
+    PCC_CUDA(cudaStreamWaitEvent(s, idx->ev_join, 0));
+    knn_wide_kernel<<<148 * 2, 128, 0, s>>>(g, v, k, oi, od, fix, fix.late_list, fix.late_count, 0);      // what the ring pass handed on (rare)
     PCC_LAUNCHED();
     knn_fixup_kernel<K><<<148 * 4, 128, 0, s>>>(g, v, k, oi, od, vec4, fix);
     PCC_LAUNCHED();
@@ -921,11 +928,11 @@ static int knn_impl(pcc_index *idx, const void *q, int64_t nq, int stride_bytes,
         // per-thread walk even at 80 queries per cell (profiles/r1/cell_kernel_probe.jsonl), so it is never chosen automatically.
         const char *cell_env = getenv("PCC_CELL_KERNEL");
         const bool use_cell = cell_env && atoi(cell_env) != 0;
-        FixList fix{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        FixList fix{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
         if (k > 1 && k <= 32 && !exact_only) {
-            PCC_TRY(idx->misc.reserve((size_t)v.nq * 13 + 256));
-            fix.count = idx->misc.as<unsigned>(); fix.ring_count = fix.count + 1; fix.wide_count = fix.count + 30;
-            fix.list = idx->misc.as<uint32_t>() + 32; fix.ring_list = fix.list + v.nq; fix.wide_list = fix.ring_list + v.nq; fix.ring_flag = (uint8_t *)(fix.wide_list + v.nq);
+            PCC_TRY(idx->misc.reserve((size_t)v.nq * 17 + 256));
+            fix.count = idx->misc.as<unsigned>(); fix.ring_count = fix.count + 1; fix.wide_count = fix.count + 30; fix.late_count = fix.count + 31;
+            fix.list = idx->misc.as<uint32_t>() + 32; fix.ring_list = fix.list + v.nq; fix.wide_list = fix.ring_list + v.nq; fix.late_list = fix.wide_list + v.nq; fix.ring_flag = (uint8_t *)(fix.late_list + v.nq);
             if (want_stats) { fix.stats = (unsigned long long *)(idx->misc.as<uint32_t>() + 2); PCC_CUDA(cudaMemsetAsync(fix.stats, 0, 112, s)); }
         }
         if (k == 1) launch_knn_reg<1>(g, v, k, oi, od, vec4, s);
