@@ -275,7 +275,7 @@ def run_ours(args):
                     "steps": e2e_steps, "how": "pcc_knn(PCC_HOST) with pinned host query / result buffers; H2D + sort + kernel + D2H inside the timed region", "checksum": checksum},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": f"pcc::knn_fast_kernel<{args.k}> (+ knn_fixup_kernel for tie overflow)", "kernel_ms": kernel_ms, "bytes_per_query": bytes_per_query, "peak_source": peak_src,
+                         "kernel": f"pcc::knn_fast_kernel<{args.k}> + the passes that finish what it lists (DeviceSelect, knn_rings_kernel, knn_wide_kernel x2, knn_fixup_kernel), timed together", "kernel_ms": kernel_ms, "bytes_per_query": bytes_per_query, "peak_source": peak_src,
                          "how": "algorithmic bytes Q*(16*N/Q + 16 + 8k) / mean kernel time over the same steps re-run with library-side CUDA events around the launch"},
             "build_ms": build_ms, "grid": grid,
         }

@@ -142,10 +142,9 @@ static double occupancy_target(int k_hint) {
     const char *e = getenv("PCC_OCC");
     if (e && atof(e) > 0) return atof(e);
     int k = k_hint > 0 ? k_hint : 16;
-    if (k == 1) return 1.0;
     // Measured on B200 (10 M queries on a 10 M-point surface cloud, kNN ms at target 4 / 6 / 8 / 10 / 12): k = 4: 3.46 / 2.60 /
     // 2.21 / - / -, k = 8: 4.31 / 3.14 / 2.71 / 2.76 / -, k = 16: - / 4.89 / 4.13 / 4.17 / 4.15, k = 32 at 12 / 16 / 20: 9.47 / 9.52 /
-    // 10.4.  With ~8 points per occupied cell the 3x3x3 block settles >80 % of the queries for k <= 16; smaller cells send too
+    // 10.4; k = 1 (own kernel) at 3 / 4 / 8: 2.68 / 2.36 / 1.80.  With ~8 points per occupied cell the 3x3x3 block settles >80 % of the queries for k <= 16; smaller cells send too
     // many of them to the ring passes, larger ones make the block walk longer.
     return std::max(8.0, 0.5 * k);
 }
