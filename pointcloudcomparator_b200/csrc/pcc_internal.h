@@ -65,7 +65,7 @@ struct pcc_index {
     pcc::Buf occ;             // uint32 [n_cells / 32 + 2]: one bit per cell, set when the cell holds a point (derived from cell_start)
     bool occ_valid = false;
     // scratch (grow-only, reused by every call on this index; calls on one index are serialised by the caller per stream)
-    pcc::Buf raw, stage4, cellrank, qbuf, qkeys, qkeys2, qperm, qperm2, cub_tmp, out_i, out_f, out_l, keys64, keys64b, misc, parent, inv_pos;
+    pcc::Buf raw, stage4, cellrank, qbuf, qkeys, qkeys2, qperm, qperm2, cub_tmp, out_i, out_f, out_l, keys64, keys64b, misc, parent, inv_pos, sel_params;
     bool inv_valid = false;   // inv_pos (original row -> sorted position) is built lazily by the consumers that need it
     void *h_pinned = nullptr;  // 4 KiB pinned scratch for scalar read-backs
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -105,6 +105,8 @@ int prepare_queries(pcc_index *idx, const void *q, int64_t nq, int stride_bytes,
 int copy_out(void *dst, const void *src_dev, size_t bytes, int mem, cudaStream_t s);
 int rebuild_inverse(pcc_index *idx, cudaStream_t s);
 int rebuild_occupancy(pcc_index *idx, cudaStream_t s);   // occ bitmap from cell_start (after pcc_build / pcc_adopt)
+// k > 32: neighbours by selection (pcc_radius.cu); rows are sorted by (d2, index), oi / od are device pointers
+int knn_select(pcc_index *idx, const Queries &qs, int k, int32_t *oi, float *od, cudaStream_t s);
 struct KernelTimer {
     pcc_index *idx; cudaStream_t s;
     KernelTimer(pcc_index *i, cudaStream_t st) : idx(i), s(st) { if (idx->timing) cudaEventRecord(idx->ev0, s); }

@@ -948,6 +948,7 @@ static int knn_impl(pcc_index *idx, const void *q, int64_t nq, int stride_bytes,
         else if (k <= 8) PCC_TRY(launch_knn_fast<8>(idx, g, v, k, oi, od, vec4, fix, s));
         else if (k <= 16) PCC_TRY(launch_knn_fast<16>(idx, g, v, k, oi, od, vec4, fix, s));
         else if (k <= 32) PCC_TRY(launch_knn_fast<32>(idx, g, v, k, oi, od, vec4, fix, s));
+        else if (!exact_only) PCC_TRY(knn_select(idx, qs, k, oi, od, s));      // 32 < k: bracket the k-th distance, then fill + sort rows
         else {
             const int th = heap_threads(k);
             PCC_TRY(set_heap_smem(knn_heap_kernel));

@@ -113,6 +113,160 @@ __global__ void __launch_bounds__(kRowSortWarps * 32) sort_rows_kernel(const int
     }
     for (int i = lane; i < n; i += 32) k[i] = sm[i];
 }
+// ---- k nearest neighbours by SELECTION, 32 < k <= PCC_MAX_K (the reference's own k: 50, 51, 100) ----
+// A per-thread heap of k 64-bit keys in shared memory (knn_heap_kernel) pays a log(k) sift of 8-byte entries per
+// accepted candidate.  Here the k-th distance is bracketed first and the neighbours are then produced like a radius
+// search whose radius is per query:
+//   bound  -- histogram of the block's squared distances below the covered radius (64 buckets, shared memory, one
+//             load-add-store per candidate); the first bucket B whose cumulative count reaches k brackets the k-th
+//             distance, and that count m (>= k, a few percent above) is the row length.  Too few points below the
+//             covered radius -> the block grows and the histogram is rebuilt,
+//   fill   -- after a prefix sum over m: re-walk the block clipped to the ball of bucket B's upper edge and emit the
+//             packed (d2, idx) keys of every point whose bucket is <= B (the same expression as in `bound`),
+//   sort   -- one warp per row (sort_csr_rows), the CSR machinery of the radius search,
+// and the consumer takes the first k keys of each row: exact, canonical (d2, index) order.
+constexpr int kSelBuckets = 64;
+struct SelParam { float scale; int bucket; int R; int pad; };
+__global__ void __launch_bounds__(128) select_bound_kernel(Grid g, QueryView v, int k, int64_t *__restrict__ counts, SelParam *__restrict__ params) {
+    __shared__ uint32_t hist_all[kSelBuckets * 128];
+    uint32_t *hist = hist_all + threadIdx.x;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float x, y, z; int64_t row;
+    if (!load_query(g, v, t, x, y, z, row)) return;      // counts are pre-zeroed
+    const QueryCell c = locate(g, x, y, z);
+    int R = 1, B = -1;
+    unsigned m = 0;
+    float scale = 0.f;
+    for (;;) {
+        const float cov = covered_d2(g, c, R);
+        float hi = cov;
+        if (cov == CUDART_INF_F) {          // the block holds the whole cloud: bracket by the largest distance instead
+            float mx = 0.f;
+            scan_shell(g, c, -1, R, [&](uint32_t, float4 p) { mx = fmaxf(mx, dist2(x, y, z, p.x, p.y, p.z)); });
+            hi = fmaxf(mx * 1.0001f, 1e-30f);
+            if (!(hi < CUDART_INF_F)) hi = 3.0e38f;
+        }
+        unsigned seen = 0;
+        if (hi > 0.f) {
+            scale = (float)kSelBuckets / hi;
+#pragma unroll 8
+            for (int b = 0; b < kSelBuckets; ++b) hist[b * 128] = 0u;
+            scan_shell(g, c, -1, R, [&](uint32_t, float4 p) {
+                const float fb = __fmul_rn(dist2(x, y, z, p.x, p.y, p.z), scale);
+                if (fb < (float)kSelBuckets) hist[(int)fb * 128] += 1u;
+            });
+            for (int b = 0; b < kSelBuckets; ++b) { seen += hist[b * 128]; if (seen >= (unsigned)k) { B = b; break; } }
+        }
+        if (B >= 0) { m = seen; break; }
+        if (cov == CUDART_INF_F) { B = kSelBuckets - 1; m = seen; break; }      // fewer than k points in the cloud: all of them
+        R = seen > 0 ? R + 1 : next_ring(g, R, CUDART_INF_F);
+    }
+    counts[row] = (m + 3u) & ~3u;          // rows are padded with empty keys to a multiple of 4: 32-byte aligned 32-byte stores in the fill
+    SelParam sp; sp.scale = scale; sp.bucket = B; sp.R = R; sp.pad = 0;
+    params[row] = sp;
+}
+__global__ void __launch_bounds__(128) select_fill_kernel(Grid g, QueryView v, const int64_t *__restrict__ offsets, const SelParam *__restrict__ params, nkey_t *__restrict__ keys) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float x, y, z; int64_t row;
+    if (!load_query(g, v, t, x, y, z, row)) return;
+    if (offsets[row + 1] == offsets[row]) return;
+    const SelParam sp = params[row];
+    const QueryCell c = locate(g, x, y, z);
+    ulonglong2 *o = reinterpret_cast<ulonglong2 *>(keys + offsets[row]);       // offsets are multiples of 4 keys
+    const float edge = (float)(sp.bucket + 1) / sp.scale;          // every selected point has d2 * scale < bucket + 1
+    const float limit = (float)(sp.bucket + 1);
+    // four keys are gathered in registers and leave as one aligned 32-byte piece: one key per store made this kernel
+    // store-bound (9 sectors per request, 3.3 GB of L2 write traffic for 0.9 GB of keys)
+    nkey_t p0 = PCC_EMPTY_KEY, p1 = PCC_EMPTY_KEY, p2 = PCC_EMPTY_KEY, p3 = PCC_EMPTY_KEY;
+    int n = 0;
+    scan_clipped(g, c, -1, sp.R, to_cell_units(g, edge * 1.00001f), [&](uint32_t, float4 p) {
+        const float d2 = dist2(x, y, z, p.x, p.y, p.z);
+        const float fb = __fmul_rn(d2, sp.scale);
+        if (fb < (float)kSelBuckets && (float)(int)fb < limit) {
+            const nkey_t key = make_key(d2, __float_as_uint(p.w));
+            const int slot = n & 3;
+            if (slot == 0) p0 = key; else if (slot == 1) p1 = key; else if (slot == 2) p2 = key; else p3 = key;
+            ++n;
+            if (slot == 3) { o[0] = make_ulonglong2(p0, p1); o[1] = make_ulonglong2(p2, p3); o += 2; p0 = p1 = p2 = p3 = PCC_EMPTY_KEY; }
+        }
+    });
+    if (n & 3) { o[0] = make_ulonglong2(p0, p1); o[1] = make_ulonglong2(p2, p3); }
+}
+// first k keys of every row -> the dense [rows, k] result, (-1, +inf) padded
+__global__ void select_unpack_kernel(const int64_t *__restrict__ offsets, const nkey_t *__restrict__ keys, int64_t rows, int k, int32_t *__restrict__ idx, float *__restrict__ d2) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * k) return;
+    const int64_t row = i / k; const int j = (int)(i - row * k);
+    const int64_t b = offsets[row], e = offsets[row + 1];
+    const nkey_t key = b + j < e ? keys[b + j] : PCC_EMPTY_KEY;
+    idx[i] = key_idx(key); d2[i] = key_d2(key);
+}
+// Rows of the selection path are k plus a few keys long: sort them in REGISTERS, 2 or 4 keys per lane (element e = r * 32 +
+// lane), partners below stride 32 through shuffles and above it inside the lane, and write the first k straight into the
+// dense result -- no shared memory, no barriers, no second pass over the keys.  Rows above 256 keys (k > ~240, heavy ties) are counted
+// and left to the generic row sort.
+template <int KPL>
+__device__ __forceinline__ void warp_sort_regs(nkey_t (&v)[KPL], int lane) {
+    constexpr int N = 32 * KPL;
+#pragma unroll
+    for (int kk = 2; kk <= N; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int jj = j >> 5;
+#pragma unroll
+                for (int r = 0; r < KPL; ++r) {
+                    if ((r & jj) == 0) {
+                        const nkey_t a = v[r], b = v[r | jj];
+                        const bool up = (((r << 5) | lane) & kk) == 0;
+                        const bool sw = (b < a) == up;
+                        v[r] = sw ? b : a; v[r | jj] = sw ? a : b;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < KPL; ++r) {
+                    const nkey_t o = __shfl_xor_sync(0xffffffffu, v[r], j);
+                    const bool up = (((r << 5) | lane) & kk) == 0, lower = (lane & j) == 0;
+                    v[r] = ((lower == up) == (o < v[r])) ? o : v[r];
+                }
+            }
+        }
+    }
+}
+template <int KPL>
+__device__ __forceinline__ void sort_unpack_row(const nkey_t *__restrict__ k_in, int n, int k, int lane, int32_t *__restrict__ oi, float *__restrict__ od) {
+    nkey_t v[KPL];
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) v[r] = (r * 32 + lane) < n ? k_in[r * 32 + lane] : PCC_EMPTY_KEY;
+    warp_sort_regs<KPL>(v, lane);
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) { const int e = r * 32 + lane; if (e < k) { oi[e] = key_idx(v[r]); od[e] = key_d2(v[r]); } }
+}
+__global__ void __launch_bounds__(128) select_sort_unpack_kernel(const int64_t *__restrict__ offsets, const nkey_t *__restrict__ keys, int64_t rows, int k,
+                                                                 int32_t *__restrict__ idx, float *__restrict__ d2, unsigned *__restrict__ n_long) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int64_t b = offsets[row], n64 = offsets[row + 1] - b;
+    int32_t *oi = idx + row * k; float *od = d2 + row * k;
+    if (n64 > 256) { if (lane == 0) atomicAdd(n_long, 1u); return; }
+    const int n = (int)n64;
+    if (n <= 32) {
+        nkey_t v[1] = {lane < n ? keys[b + lane] : PCC_EMPTY_KEY};
+        warp_sort_regs<1>(v, lane);
+        for (int e = lane; e < k; e += 32) { oi[e] = e < 32 ? key_idx(v[0]) : -1; od[e] = e < 32 ? key_d2(v[0]) : CUDART_INF_F; }
+    } else if (n <= 64) {
+        sort_unpack_row<2>(keys + b, n, k, lane, oi, od);
+        for (int e = 64 + lane; e < k; e += 32) { oi[e] = -1; od[e] = CUDART_INF_F; }
+    } else if (n <= 128) {
+        sort_unpack_row<4>(keys + b, n, k, lane, oi, od);
+        for (int e = 128 + lane; e < k; e += 32) { oi[e] = -1; od[e] = CUDART_INF_F; }
+    } else {
+        sort_unpack_row<8>(keys + b, n, k, lane, oi, od);
+        for (int e = 256 + lane; e < k; e += 32) { oi[e] = -1; od[e] = CUDART_INF_F; }
+    }
+}
 __global__ void big_row_bounds_kernel(const int64_t *__restrict__ offsets, const uint32_t *__restrict__ big_rows, unsigned n_big, int64_t *__restrict__ begin, int64_t *__restrict__ end) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_big) { begin[i] = offsets[big_rows[i]]; end[i] = offsets[big_rows[i] + 1]; }
@@ -261,27 +415,10 @@ static int radius_offsets(pcc_index *idx, const Queries &qs, double radius, unsi
     g_launches += 2;
     return PCC_OK;
 }
-// rows as packed keys into idx->keys64 (sorted in place when requested); total = offsets[rows]
-static int radius_rows(pcc_index *idx, const Queries &qs, double radius, unsigned max_nn, int sorted, const int64_t *d_offsets, int64_t total, nkey_t **keys_out, cudaStream_t s) {
-    const float r2 = (float)(radius * radius);
-    PCC_TRY(idx->keys64.reserve((size_t)std::max<int64_t>(total, 1) * sizeof(nkey_t)));
-    nkey_t *keys = idx->keys64.as<nkey_t>();
-    *keys_out = keys;
-    if (qs.nq == 0 || total == 0) return PCC_OK;
-    const bool capped = max_nn != 0 && (int64_t)max_nn < idx->n_indexed;
-    if (capped) {
-        if (max_nn > PCC_MAX_K) return fail(PCC_ERR_INVALID, "max_nn=%u above %d is only supported when it is >= the indexed point count", max_nn, PCC_MAX_K);
-        const int th = heap_threads((int)max_nn);
-        PCC_CUDA(cudaFuncSetAttribute(radius_capped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        radius_capped_kernel<<<nblocks(qs.nq, th), th, (size_t)max_nn * th * sizeof(nkey_t), s>>>(idx->grid(), view_of(qs), r2, ring0(idx, radius), (int)max_nn, d_offsets, keys);
-        PCC_LAUNCHED();
-        PCC_CUDA(cudaGetLastError());
-        return PCC_OK;   // already sorted
-    }
-    radius_fill_kernel<<<nblocks(qs.nq, 128), 128, 0, s>>>(idx->grid(), view_of(qs), r2, ring0(idx, radius), d_offsets, keys);
-    PCC_LAUNCHED();
-    PCC_CUDA(cudaGetLastError());
-    if (sorted) {
+// every CSR row sorted by its packed (d2, idx) key: one warp per row, rows above 1024 keys by the library afterwards
+static int sort_csr_rows(pcc_index *idx, int64_t rows, const int64_t *d_offsets, int64_t total, nkey_t *keys, cudaStream_t s) {
+    Queries qs; qs.rows = rows;
+    {
         PCC_TRY(idx->misc.reserve((size_t)qs.rows * 4 + 64));
         unsigned *n_big = idx->misc.as<unsigned>();
         uint32_t *big_rows = idx->misc.as<uint32_t>() + 16;
@@ -307,6 +444,83 @@ static int radius_rows(pcc_index *idx, const Queries &qs, double radius, unsigne
             big_row_copy_kernel<<<nb, 256, 0, s>>>(bb, be, idx->keys64b.as<nkey_t>(), keys); PCC_LAUNCHED();
             PCC_CUDA(cudaGetLastError());
         }
+    }
+    return PCC_OK;
+}
+// rows as packed keys into idx->keys64 (sorted in place when requested); total = offsets[rows]
+static int radius_rows(pcc_index *idx, const Queries &qs, double radius, unsigned max_nn, int sorted, const int64_t *d_offsets, int64_t total, nkey_t **keys_out, cudaStream_t s) {
+    const float r2 = (float)(radius * radius);
+    PCC_TRY(idx->keys64.reserve((size_t)std::max<int64_t>(total, 1) * sizeof(nkey_t)));
+    nkey_t *keys = idx->keys64.as<nkey_t>();
+    *keys_out = keys;
+    if (qs.nq == 0 || total == 0) return PCC_OK;
+    const bool capped = max_nn != 0 && (int64_t)max_nn < idx->n_indexed;
+    if (capped) {
+        if (max_nn > PCC_MAX_K) return fail(PCC_ERR_INVALID, "max_nn=%u above %d is only supported when it is >= the indexed point count", max_nn, PCC_MAX_K);
+        const int th = heap_threads((int)max_nn);
+        PCC_CUDA(cudaFuncSetAttribute(radius_capped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        radius_capped_kernel<<<nblocks(qs.nq, th), th, (size_t)max_nn * th * sizeof(nkey_t), s>>>(idx->grid(), view_of(qs), r2, ring0(idx, radius), (int)max_nn, d_offsets, keys);
+        PCC_LAUNCHED();
+        PCC_CUDA(cudaGetLastError());
+        return PCC_OK;   // already sorted
+    }
+    radius_fill_kernel<<<nblocks(qs.nq, 128), 128, 0, s>>>(idx->grid(), view_of(qs), r2, ring0(idx, radius), d_offsets, keys);
+    PCC_LAUNCHED();
+    PCC_CUDA(cudaGetLastError());
+    if (sorted) PCC_TRY(sort_csr_rows(idx, qs.rows, d_offsets, total, keys, s));
+    return PCC_OK;
+}
+
+// sorted neighbour rows for k > 32: d_offsets (rows + 1, device) and keys (idx->keys64); every row holds >= min(k, cloud) keys
+int knn_select_rows(pcc_index *idx, const Queries &qs, int k, int64_t *d_offsets, nkey_t **keys_out, int64_t *total_out, bool sort_rows, cudaStream_t s) {
+    PCC_TRY(idx->sel_params.reserve((size_t)std::max<int64_t>(qs.rows, 1) * sizeof(SelParam)));
+    SelParam *params = idx->sel_params.as<SelParam>();
+    PCC_CUDA(cudaMemsetAsync(d_offsets, 0, (size_t)(qs.rows + 1) * sizeof(int64_t), s));
+    if (qs.nq > 0) {
+        select_bound_kernel<<<nblocks(qs.nq, 128), 128, 0, s>>>(idx->grid(), view_of(qs), k, d_offsets, params);
+        PCC_LAUNCHED();
+        PCC_CUDA(cudaGetLastError());
+    }
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_offsets, d_offsets, (int)(qs.rows + 1), s);
+    PCC_TRY(idx->cub_tmp.reserve(tmp));
+    PCC_CUDA(cub::DeviceScan::ExclusiveSum(idx->cub_tmp.p, tmp, d_offsets, d_offsets, (int)(qs.rows + 1), s));
+    g_launches += 2;
+    int64_t *h = (int64_t *)idx->h_pinned;
+    PCC_CUDA(cudaMemcpyAsync(h, d_offsets + qs.rows, 8, cudaMemcpyDeviceToHost, s));
+    PCC_CUDA(cudaStreamSynchronize(s));
+    const int64_t total = h[0];
+    *total_out = total;
+    PCC_TRY(idx->keys64.reserve((size_t)std::max<int64_t>(total, 1) * sizeof(nkey_t)));
+    nkey_t *keys = idx->keys64.as<nkey_t>();
+    *keys_out = keys;
+    if (qs.nq == 0 || total == 0) return PCC_OK;
+    select_fill_kernel<<<nblocks(qs.nq, 128), 128, 0, s>>>(idx->grid(), view_of(qs), d_offsets, params, keys);
+    PCC_LAUNCHED();
+    PCC_CUDA(cudaGetLastError());
+    return sort_rows ? sort_csr_rows(idx, qs.rows, d_offsets, total, keys, s) : PCC_OK;
+}
+// pcc_knn for k > 32
+int knn_select(pcc_index *idx, const Queries &qs, int k, int32_t *oi, float *od, cudaStream_t s) {
+    PCC_TRY(idx->out_l.reserve((size_t)(qs.rows + 1) * 8));
+    int64_t *d_off = idx->out_l.as<int64_t>();
+    nkey_t *keys = nullptr; int64_t total = 0;
+    PCC_TRY(knn_select_rows(idx, qs, k, d_off, &keys, &total, false, s));
+    if (qs.rows == 0) return PCC_OK;
+    PCC_TRY(idx->misc.reserve(256));
+    unsigned *n_long = idx->misc.as<unsigned>();
+    PCC_CUDA(cudaMemsetAsync(n_long, 0, 4, s));
+    select_sort_unpack_kernel<<<nblocks(qs.rows, 4), 128, 0, s>>>(d_off, keys, qs.rows, k, oi, od, n_long);
+    PCC_LAUNCHED();
+    PCC_CUDA(cudaGetLastError());
+    unsigned *h = (unsigned *)idx->h_pinned;
+    PCC_CUDA(cudaMemcpyAsync(h, n_long, 4, cudaMemcpyDeviceToHost, s));
+    PCC_CUDA(cudaStreamSynchronize(s));
+    if (h[0] > 0) {         // rows above 256 keys (large k, or many points tied inside the bracketing bucket): generic row sort, then unpack everything
+        PCC_TRY(sort_csr_rows(idx, qs.rows, d_off, total, keys, s));
+        select_unpack_kernel<<<nblocks(qs.rows * (int64_t)k, 256), 256, 0, s>>>(d_off, keys, qs.rows, k, oi, od);
+        PCC_LAUNCHED();
+        PCC_CUDA(cudaGetLastError());
     }
     return PCC_OK;
 }

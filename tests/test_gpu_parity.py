@@ -527,3 +527,21 @@ def test_knn_adopted_grid_rebuilds_occupancy(GS):
     gi, gd, _ = b.nearestKSearch(qry, 8)
     oi, od, _ = oracle.KdTree(ref).knn(qry, 8)
     assert_knn_equal(gi, gd, oi, od)
+
+
+@pytest.mark.parametrize("k", [40, 64, 120, 200, 257, 512])
+def test_knn_large_k_selection_path(GS, k):
+    """k > 32: the k-th distance is bracketed by a histogram, the rows are filled like a radius search and sorted in
+    registers (<= 256 keys) or by the generic row sort; far queries, duplicates and a cloud smaller than some blocks."""
+    rng = np.random.default_rng(300 + k)
+    ref = np.concatenate([synth.room(20000, 5), rng.normal(2.0, 0.02, (600, 3)), np.repeat(rng.uniform(0, 3, (5, 3)), 70, axis=0)]).astype(np.float32)
+    qry = np.concatenate([ref[::11] + rng.normal(0, 0.01, (len(ref[::11]), 3)), rng.uniform(-3, 8, (300, 3)), [[np.nan, 0, 0], [60, 60, 60]]]).astype(np.float32)
+    s = GS().setInputCloud(ref, k_hint=k)
+    gi, gd, _ = s.nearestKSearch(qry, k)
+    oi, od, _ = oracle.brute_knn(ref, qry, k)          # canonical (d2, index) order: 70-fold duplicates tie far beyond k
+    assert_knn_equal(gi, gd, oi, od)
+    small = ref[:100]
+    gi, gd, keff = GS().setInputCloud(small, k_hint=k).nearestKSearch(qry[:50], k)       # k > cloud size: padded rows
+    oi, od, okeff = oracle.brute_knn(small, qry[:50], k)
+    assert keff == okeff == min(k, 100)
+    assert_knn_equal(gi, gd, oi, od)
