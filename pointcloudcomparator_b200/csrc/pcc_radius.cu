@@ -50,7 +50,24 @@ __global__ void __launch_bounds__(128) radius_fill_kernel(Grid g, QueryView v, f
     float x, y, z; int64_t row;
     if (!load_query(g, v, t, x, y, z, row)) return;
     nkey_t *o = keys + offsets[row];
-    radius_visit(g, x, y, z, r2, R0, [&](uint32_t, float4 p, float d2) { *o++ = make_key(d2, __float_as_uint(p.w)); });
+    // One 8-byte store per neighbour made this kernel store-bound (every lane writes into its own row: 32 sectors per
+    // request).  Keys leave four at a time as one 32-byte aligned piece; the 0-3 keys before the row's first aligned
+    // address and the 0-3 left at the end are stored singly.
+    int lead = (int)((4u - (unsigned)(((uintptr_t)o >> 3) & 3u)) & 3u);
+    nkey_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+    int n = 0;
+    radius_visit(g, x, y, z, r2, R0, [&](uint32_t, float4 p, float d2) {
+        const nkey_t key = make_key(d2, __float_as_uint(p.w));
+        if (lead > 0) { *o++ = key; --lead; return; }
+        const int slot = n & 3;
+        if (slot == 0) p0 = key; else if (slot == 1) p1 = key; else if (slot == 2) p2 = key; else p3 = key;
+        ++n;
+        if (slot == 3) { reinterpret_cast<ulonglong2 *>(o)[0] = make_ulonglong2(p0, p1); reinterpret_cast<ulonglong2 *>(o)[1] = make_ulonglong2(p2, p3); o += 4; }
+    });
+    const int rest = n & 3;
+    if (rest > 0) o[0] = p0;
+    if (rest > 1) o[1] = p1;
+    if (rest > 2) o[2] = p2;
 }
 // max_nn-capped rows: keep the max_nn smallest keys in a shared-memory heap, emit them sorted
 __global__ void radius_capped_kernel(Grid g, QueryView v, float r2, int R0, int max_nn, const int64_t *__restrict__ offsets, nkey_t *__restrict__ keys) {
@@ -68,6 +85,46 @@ __global__ void radius_capped_kernel(Grid g, QueryView v, float r2, int R0, int 
 // cub::DeviceSegmentedSort took 475 ms for 722 M keys in 5 M rows of ~144 (its large-segment path, one block per row);
 // radius rows are short, so one WARP sorts one row: <= 32 keys in registers with shuffles, <= 1024 keys with a bitonic
 // network in the warp's shared-memory slice.  Longer rows are listed and sorted by the library afterwards.
+// bitonic network over 32 * KPL keys held KPL per lane (element e = r * 32 + lane): partners below stride 32 through
+// shuffles, above it inside the lane
+template <int KPL>
+__device__ __forceinline__ void warp_sort_regs(nkey_t (&v)[KPL], int lane) {
+    constexpr int N = 32 * KPL;
+#pragma unroll
+    for (int kk = 2; kk <= N; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int jj = j >> 5;
+#pragma unroll
+                for (int r = 0; r < KPL; ++r) {
+                    if ((r & jj) == 0) {
+                        const nkey_t a = v[r], b = v[r | jj];
+                        const bool up = (((r << 5) | lane) & kk) == 0;
+                        const bool sw = (b < a) == up;
+                        v[r] = sw ? b : a; v[r | jj] = sw ? a : b;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < KPL; ++r) {
+                    const nkey_t o = __shfl_xor_sync(0xffffffffu, v[r], j);
+                    const bool up = (((r << 5) | lane) & kk) == 0, lower = (lane & j) == 0;
+                    v[r] = ((lower == up) == (o < v[r])) ? o : v[r];
+                }
+            }
+        }
+    }
+}
+template <int KPL>
+__device__ __forceinline__ void sort_row_in_place(nkey_t *__restrict__ k, int n, int lane) {
+    nkey_t v[KPL];
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) v[r] = (r * 32 + lane) < n ? k[r * 32 + lane] : PCC_EMPTY_KEY;
+    warp_sort_regs<KPL>(v, lane);
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) if ((r * 32 + lane) < n) k[r * 32 + lane] = v[r];
+}
 static constexpr int kRowSortWarps = 4, kRowSortCap = 1024;
 __global__ void __launch_bounds__(kRowSortWarps * 32) sort_rows_kernel(const int64_t *__restrict__ offsets, int64_t rows, nkey_t *__restrict__ keys,
                                                                        uint32_t *__restrict__ big_rows, unsigned *__restrict__ n_big) {
@@ -96,6 +153,11 @@ __global__ void __launch_bounds__(kRowSortWarps * 32) sort_rows_kernel(const int
         if (lane < n) k[lane] = v;
         return;
     }
+    // up to 256 keys: registers and shuffles, no shared memory and no barriers (measured on the selection path: 2.7 ms
+    // -> 0.95 ms for 2 M rows of ~55 keys); longer rows: bitonic network in the warp's shared-memory slice
+    if (n <= 64) { sort_row_in_place<2>(k, n, lane); return; }
+    if (n <= 128) { sort_row_in_place<4>(k, n, lane); return; }
+    if (n <= 256) { sort_row_in_place<8>(k, n, lane); return; }
     nkey_t *sm = sm_all[warp];
     int P = 64; while (P < n) P <<= 1;
     for (int i = lane; i < P; i += 32) sm[i] = i < n ? k[i] : PCC_EMPTY_KEY;
@@ -201,39 +263,9 @@ __global__ void select_unpack_kernel(const int64_t *__restrict__ offsets, const 
     const nkey_t key = b + j < e ? keys[b + j] : PCC_EMPTY_KEY;
     idx[i] = key_idx(key); d2[i] = key_d2(key);
 }
-// Rows of the selection path are k plus a few keys long: sort them in REGISTERS, 2 or 4 keys per lane (element e = r * 32 +
-// lane), partners below stride 32 through shuffles and above it inside the lane, and write the first k straight into the
-// dense result -- no shared memory, no barriers, no second pass over the keys.  Rows above 256 keys (k > ~240, heavy ties) are counted
-// and left to the generic row sort.
-template <int KPL>
-__device__ __forceinline__ void warp_sort_regs(nkey_t (&v)[KPL], int lane) {
-    constexpr int N = 32 * KPL;
-#pragma unroll
-    for (int kk = 2; kk <= N; kk <<= 1) {
-#pragma unroll
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            if (j >= 32) {
-                const int jj = j >> 5;
-#pragma unroll
-                for (int r = 0; r < KPL; ++r) {
-                    if ((r & jj) == 0) {
-                        const nkey_t a = v[r], b = v[r | jj];
-                        const bool up = (((r << 5) | lane) & kk) == 0;
-                        const bool sw = (b < a) == up;
-                        v[r] = sw ? b : a; v[r | jj] = sw ? a : b;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < KPL; ++r) {
-                    const nkey_t o = __shfl_xor_sync(0xffffffffu, v[r], j);
-                    const bool up = (((r << 5) | lane) & kk) == 0, lower = (lane & j) == 0;
-                    v[r] = ((lower == up) == (o < v[r])) ? o : v[r];
-                }
-            }
-        }
-    }
-}
+// Rows of the selection path are k plus a few keys long: sort them in REGISTERS (warp_sort_regs, 2 / 4 / 8 keys per lane)
+// and write the first k straight into the dense result -- no shared memory, no barriers, no second pass over the keys.
+// Rows above 256 keys (k > ~240, heavy ties) are counted and left to the generic row sort.
 template <int KPL>
 __device__ __forceinline__ void sort_unpack_row(const nkey_t *__restrict__ k_in, int n, int k, int lane, int32_t *__restrict__ oi, float *__restrict__ od) {
     nkey_t v[KPL];
