@@ -243,7 +243,7 @@ void pcc_destroy(pcc_index *idx) {
     if (idx->shadow) { pcc_index *sh = idx->shadow; idx->shadow = nullptr; pcc_destroy(sh); }
     for (int i = 0; i < 2; ++i) if (idx->pipe_stream[i]) cudaStreamDestroy(idx->pipe_stream[i]);
     Buf *bufs[] = {&idx->pts, &idx->cell_start, &idx->occ, &idx->raw, &idx->stage4, &idx->cellrank, &idx->qbuf, &idx->qkeys, &idx->qkeys2, &idx->qperm, &idx->qperm2,
-                   &idx->cub_tmp, &idx->out_i, &idx->out_f, &idx->out_l, &idx->keys64, &idx->keys64b, &idx->misc, &idx->parent, &idx->inv_pos, &idx->sel_params};
+                   &idx->cub_tmp, &idx->out_i, &idx->out_f, &idx->out_l, &idx->keys64, &idx->keys64b, &idx->misc, &idx->parent, &idx->inv_pos, &idx->sel_params, &idx->icp_prior};
     for (Buf *b : bufs) b->release();
     if (idx->h_pinned) cudaFreeHost(idx->h_pinned);
     if (idx->aux_stream) cudaStreamDestroy(idx->aux_stream);
@@ -275,6 +275,7 @@ int pcc_build(pcc_index *idx, const void *pts, int64_t n, int stride_bytes, cons
     idx->built = false;
     idx->inv_valid = false;
     idx->occ_valid = false;
+    idx->icp_prior_n = -1;
     const int64_t m = indices ? n_idx : n;
     idx->n_input = n;                 // labels / self-query rows are addressed by ORIGINAL row number
     idx->n_indexed = 0;
@@ -416,6 +417,7 @@ int pcc_adopt(pcc_index *idx, const double meta[16], void *stream) {
     PCC_TRY(idx->cell_start.reserve((size_t)(idx->gh.n_cells + 1) * sizeof(uint32_t)));
     idx->built = true;
     idx->inv_valid = false;
+    idx->icp_prior_n = -1;
     idx->occ_valid = false;       // the caller fills the arrays after this call: the bitmap is derived on the first query
     return PCC_OK;
 }

@@ -734,8 +734,14 @@ struct Mat34 { float m[12]; };
 static constexpr int kIcpThreads = 128;
 // One thread per source point: move it by T (IterativeClosestPoint::transformCloud arithmetic), find its nearest
 // target point, and reduce the 16 sums Umeyama needs + the correspondence count to one row of doubles per block.
+// `prior[row]` = sorted position of the target point this source row matched in the previous pass (0xFFFFFFFF = none).  ANY
+// target point is a valid upper bound for the nearest-neighbour distance, so the result does not depend on it; but between
+// two ICP iterations a point moves little, the old match is (nearly) the new one, and the search starts as ONE pass over
+// the block that covers the ball of that distance, clipped to the ball -- instead of doubling blocks outwards through
+// empty space until something is found (first iterations), or walking the whole 3x3x3 block (converged iterations).
 __global__ void __launch_bounds__(kIcpThreads) icp_step_kernel(Grid g, float4 *__restrict__ src, const uint32_t *__restrict__ order, int64_t ns, Mat34 T, int apply,
-                                                               double *__restrict__ partials, int32_t *__restrict__ corr_idx, float *__restrict__ corr_d2) {
+                                                               double *__restrict__ partials, int32_t *__restrict__ corr_idx, float *__restrict__ corr_d2,
+                                                               uint32_t *__restrict__ prior) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double acc[17];
 #pragma unroll
@@ -744,6 +750,7 @@ __global__ void __launch_bounds__(kIcpThreads) icp_step_kernel(Grid g, float4 *_
         const uint32_t qi = order ? __ldg(order + t) : (uint32_t)t;
         float4 p = src[qi];
         int32_t bi = -1; float bd = CUDART_INF_F;
+        uint32_t acc_pos = 0xFFFFFFFFu;
         if (finite3(p.x, p.y, p.z)) {
             if (apply) {   // ((m0*x + m1*y) + m2*z) + m3 in fp32; -fmad=false keeps the products separately rounded
                 float nx = ((T.m[0] * p.x + T.m[1] * p.y) + T.m[2] * p.z) + T.m[3];
@@ -756,6 +763,12 @@ __global__ void __launch_bounds__(kIcpThreads) icp_step_kernel(Grid g, float4 *_
                 nkey_t best = PCC_EMPTY_KEY; uint32_t bpos = 0;
                 const QueryCell c = locate(g, p.x, p.y, p.z);
                 int Rin = -1, R = 1;
+                const uint32_t pv = prior ? prior[qi] : 0xFFFFFFFFu;
+                if (pv < g.n) {
+                    const float4 m = __ldg(g.pts + pv);
+                    best = make_key(dist2(p.x, p.y, p.z, m.x, m.y, m.z), __float_as_uint(m.w)); bpos = pv;
+                    R = next_ring(g, 0, key_d2(best));
+                }
                 for (;;) {
                     scan_progressive(g, c, Rin, R, [&]() { return to_cell_units(g, key_d2(best)); }, [&](uint32_t pos, float4 r) {
                         const nkey_t k = make_key(dist2(p.x, p.y, p.z, r.x, r.y, r.z), __float_as_uint(r.w));
@@ -768,6 +781,7 @@ __global__ void __launch_bounds__(kIcpThreads) icp_step_kernel(Grid g, float4 *_
                 }
                 bi = key_idx(best); bd = key_d2(best);
                 if (bi >= 0) {
+                    acc_pos = bpos;
                     const float4 m = __ldg(g.pts + bpos);
                     const double sx = p.x, sy = p.y, sz = p.z, tx = m.x, ty = m.y, tz = m.z;
                     acc[0] = sx; acc[1] = sy; acc[2] = sz; acc[3] = tx; acc[4] = ty; acc[5] = tz;
@@ -780,6 +794,7 @@ __global__ void __launch_bounds__(kIcpThreads) icp_step_kernel(Grid g, float4 *_
         }
         if (corr_idx) corr_idx[qi] = bi;
         if (corr_d2) corr_d2[qi] = bd;
+        if (prior) prior[qi] = bi >= 0 ? acc_pos : 0xFFFFFFFFu;
     }
     __shared__ double red[kIcpThreads / 32][17];
 #pragma unroll
@@ -1109,7 +1124,17 @@ int pcc_icp_step(pcc_index *idx, void *src_inout, int64_t ns, int stride_bytes, 
         if (corr_d2) { PCC_TRY(idx->out_f.reserve((size_t)ns * 4)); cd = idx->out_f.as<float>(); }
     }
     KernelTimer timer(idx, s);
-    icp_step_kernel<<<nb, kIcpThreads, 0, s>>>(idx->grid(), work, qs.order, ns, T, apply, partials, ci, cd);
+    static const bool no_prior = getenv("PCC_ICP_NO_PRIOR") != nullptr;      // measurement aid
+    uint32_t *prior = nullptr;
+    if (!no_prior) {
+        if (idx->icp_prior_n != ns) {        // first pass over this source cloud (or a new index): no bounds yet
+            PCC_TRY(idx->icp_prior.reserve((size_t)std::max<int64_t>(ns, 1) * 4));
+            PCC_CUDA(cudaMemsetAsync(idx->icp_prior.p, 0xFF, (size_t)std::max<int64_t>(ns, 1) * 4, s));
+            idx->icp_prior_n = ns;
+        }
+        prior = idx->icp_prior.as<uint32_t>();
+    }
+    icp_step_kernel<<<nb, kIcpThreads, 0, s>>>(idx->grid(), work, qs.order, ns, T, apply, partials, ci, cd, prior);
     PCC_LAUNCHED();
     icp_reduce_kernel<<<17, 256, 0, s>>>(partials, nb, d_out);
     PCC_LAUNCHED();
