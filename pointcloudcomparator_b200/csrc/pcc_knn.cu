@@ -179,9 +179,7 @@ __device__ __forceinline__ void knn_fast_body(const Grid &g, const QueryView &v,
     // where an unproved query goes next: one more ring (flag), the wide pass, or the exact kernel
     const bool tied = m > K;                                                       // more than K candidates tied at tau: exact path
     const bool wide = !tied && !proved && (tau == CUDART_INF_F || next_ring(g, 1, tau) > kRingMaxR);
-#ifndef PCC_X_NOFLAG
     if (R0 == 1) fix.ring_flag[t] = (!tied && !proved && !wide) ? 1 : 0;
-#endif
     if (tied) { push_list(fix.list, fix.count, (uint32_t)t); return; }
     if (wide) { push_list(fix.wide_list, fix.wide_count, (uint32_t)t); return; }
     nkey_t e[K];
