@@ -545,3 +545,42 @@ def test_knn_large_k_selection_path(GS, k):
     oi, od, okeff = oracle.brute_knn(small, qry[:50], k)
     assert keff == okeff == min(k, 100)
     assert_knn_equal(gi, gd, oi, od)
+
+
+def test_icp_previous_match_bound_does_not_change_results(GS):
+    """pcc_icp_step starts every search from the target point matched in the previous call.  The bound must be invisible:
+    the same pass answered cold (fresh index), warm (bounds from an identical pass) and with misleading bounds (left by a
+    very different source cloud of the same size) gives identical correspondences, and they equal the oracle's 1-NN."""
+    rng = np.random.default_rng(77)
+    tgt = synth.room(60000, 9)
+    src = (tgt[rng.permutation(len(tgt))[:20000]] + rng.normal(0, 0.03, (20000, 3))).astype(np.float32)
+    other = rng.uniform(-2, 8, (20000, 3)).astype(np.float32)
+    oi, od, _ = oracle.KdTree(tgt).knn(src, 1)
+    s = GS().setInputCloud(tgt, k_hint=16)
+    cold = s.icpStep(src.copy(), None, want_correspondences=True)
+    warm = s.icpStep(src.copy(), None, want_correspondences=True)
+    s.icpStep(other.copy(), None)                                   # leaves bounds that have nothing to do with `src`
+    misled = s.icpStep(src.copy(), None, want_correspondences=True)
+    for cnt, sums, ci, cd in (cold, warm, misled):
+        assert cnt == 20000
+        assert np.array_equal(ci, oi[:, 0]) and np.array_equal(bits(cd), bits(od[:, 0]))
+        assert np.array_equal(sums, cold[1])                        # deterministic reduction: bit-identical sums
+
+
+def test_large_k_properties_2m(GS):
+    """k = 50 (the reference's NormalEstimation / SOR neighbourhood) at 2 M points through the selection path: size-
+    independent properties plus a sampled oracle check."""
+    import torch
+    ref = synth.room(2_000_000, 4001, size=(6.0, 6.0, 3.0), stride4=True)
+    dref = torch.from_numpy(ref).cuda()
+    s = GS().setInputCloud(dref, k_hint=50)
+    idx, d2, keff = s.nearestKSearch(None, 50)
+    assert keff == 50
+    assert bool((d2[:, 1:] >= d2[:, :-1]).all()) and bool((d2[:, 0] == 0).all())
+    assert bool((idx >= 0).all()) and bool((idx < ref.shape[0]).all())
+    srt = torch.sort(idx.long(), dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())
+    sample = np.random.default_rng(1).choice(ref.shape[0], 5000, replace=False)
+    oi, od, _ = oracle.KdTree(ref).knn(ref[sample], 50)
+    assert np.array_equal(idx[torch.from_numpy(sample).cuda()].cpu().numpy(), oi)
+    assert np.array_equal(bits(d2[torch.from_numpy(sample).cuda()].cpu().numpy()), bits(od))
