@@ -372,14 +372,27 @@ __global__ void __launch_bounds__(128) ece_link_kernel(Grid g, float r2, int R0,
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= g.n) return;
     const float4 q = __ldg(g.pts + t);
-    radius_visit(g, q.x, q.y, q.z, r2, R0, [&](uint32_t pos, float4, float) { if (pos < (uint32_t)t) uf_union(parent, (uint32_t)t, pos); });
+    // `ra` is an ancestor of t (its root when last looked up).  Most neighbours already hang directly under it after the
+    // first few unions, so one load of parent[pos] settles them without the two root walks of a full union.
+    uint32_t ra = uf_find(parent, (uint32_t)t);
+    radius_visit(g, q.x, q.y, q.z, r2, R0, [&](uint32_t pos, float4, float) {
+        if (pos >= (uint32_t)t) return;
+        if (pos == ra || __ldcg(parent + pos) == ra) return;
+        uf_union(parent, ra, pos);
+        ra = uf_find(parent, ra);
+    });
 }
 // sharded clustering: link only the edges whose query endpoint lies in [begin, end) of the sorted order
 __global__ void __launch_bounds__(128) ece_link_range_kernel(Grid g, float r2, int R0, uint32_t begin, uint32_t end, uint32_t *__restrict__ parent) {
     const int64_t t = (int64_t)begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= end) return;
     const float4 q = __ldg(g.pts + t);
-    radius_visit(g, q.x, q.y, q.z, r2, R0, [&](uint32_t pos, float4, float) { if (pos != (uint32_t)t) uf_union(parent, (uint32_t)t, pos); });
+    uint32_t ra = uf_find(parent, (uint32_t)t);
+    radius_visit(g, q.x, q.y, q.z, r2, R0, [&](uint32_t pos, float4, float) {
+        if (pos == (uint32_t)t || pos == ra || __ldcg(parent + pos) == ra) return;
+        uf_union(parent, ra, pos);
+        ra = uf_find(parent, ra);
+    });
 }
 // merge another rank's knowledge: node i and other[i] are in the same component
 __global__ void ece_absorb_kernel(uint32_t n, const uint32_t *__restrict__ other, uint32_t *__restrict__ parent) {
