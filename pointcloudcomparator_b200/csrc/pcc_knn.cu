@@ -729,7 +729,7 @@ __global__ void normals_knn_heap_kernel(Grid g, QueryView v, int k, const uint32
 
 // ---- fused: ICP correspondence pass ----
 struct Mat34 { float m[12]; };
-static constexpr int kIcpThreads = 128;
+static constexpr int kIcpThreads = 128, kIcpMaxPriorR = 16;
 // One thread per source point: move it by T (IterativeClosestPoint::transformCloud arithmetic), find its nearest
 // target point, and reduce the 16 sums Umeyama needs + the correspondence count to one row of doubles per block.
 // `prior[row]` = sorted position of the target point this source row matched in the previous pass (0xFFFFFFFF = none).  ANY
@@ -766,6 +766,9 @@ __global__ void __launch_bounds__(kIcpThreads) icp_step_kernel(Grid g, float4 *_
                     const float4 m = __ldg(g.pts + pv);
                     best = make_key(dist2(p.x, p.y, p.z, m.x, m.y, m.z), __float_as_uint(m.w)); bpos = pv;
                     R = next_ring(g, 0, key_d2(best));
+                    // a bound wider than kIcpMaxPriorR cells does not help (a pass costs O(R^2) rows): forget it and search
+                    // outwards as usual (the source cloud changed between calls).
+                    if (R > kIcpMaxPriorR) { best = PCC_EMPTY_KEY; bpos = 0; R = 1; }
                 }
                 for (;;) {
                     scan_progressive(g, c, Rin, R, [&]() { return to_cell_units(g, key_d2(best)); }, [&](uint32_t pos, float4 r) {
@@ -1125,7 +1128,8 @@ int pcc_icp_step(pcc_index *idx, void *src_inout, int64_t ns, int stride_bytes, 
     static const bool no_prior = getenv("PCC_ICP_NO_PRIOR") != nullptr;      // measurement aid
     uint32_t *prior = nullptr;
     if (!no_prior) {
-        if (idx->icp_prior_n != ns) {        // first pass over this source cloud (or a new index): no bounds yet
+        const bool fresh = idx->icp_prior_n != ns;        // first pass over this source cloud (or a new index): no bounds yet
+        if (fresh) {
             PCC_TRY(idx->icp_prior.reserve((size_t)std::max<int64_t>(ns, 1) * 4));
             PCC_CUDA(cudaMemsetAsync(idx->icp_prior.p, 0xFF, (size_t)std::max<int64_t>(ns, 1) * 4, s));
             idx->icp_prior_n = ns;
