@@ -178,6 +178,15 @@ int prepare_queries(pcc_index *idx, const void *q, int64_t nq, int stride_bytes,
         raw = idx->raw.as<uint8_t>();
     }
     PCC_TRY(idx->qbuf.reserve((size_t)nq * sizeof(float4)));
+    if (idx->reuse_order_n == nq && nq > 2048) {          // same rows as the previous pass, slightly moved: keep its order
+        BinParams b0{idx->gh.ox, idx->gh.oy, idx->gh.oz, idx->gh.inv_cell, idx->gh.nx, idx->gh.ny, idx->gh.nz};
+        qprep_kernel<<<blocks_for(nq, 256), 256, 0, s>>>(raw, stride_bytes, nq, b0, (uint32_t)idx->gh.n_cells, idx->qbuf.as<float4>(), nullptr, nullptr);
+        PCC_LAUNCHED();
+        PCC_CUDA(cudaGetLastError());
+        out->q = idx->qbuf.as<float4>();
+        out->order = idx->qperm2.as<uint32_t>();
+        return PCC_OK;
+    }
     const bool sort = nq > 2048;
     BinParams b{idx->gh.ox, idx->gh.oy, idx->gh.oz, idx->gh.inv_cell, idx->gh.nx, idx->gh.ny, idx->gh.nz};
     if (sort) {

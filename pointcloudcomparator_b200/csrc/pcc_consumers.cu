@@ -248,11 +248,14 @@ int pcc_icp_align(pcc_index *idx, const void *src, int64_t ns, int stride_bytes,
     }
     double prev_mse = DBL_MAX;
     const float *apply = nullptr;
+    struct OrderReset { pcc_index *i; ~OrderReset() { i->reuse_order_n = -1; } } order_reset{idx};   // also on the error returns below
+    idx->reuse_order_n = -1;
     idx->icp_prior_n = -1;        // a new alignment starts from the untransformed source: matches left by an earlier one are loose bounds (measured: first pass 31 ms with them, 17 ms without)
     static const bool trace = getenv("PCC_ICP_TRACE") != nullptr;     // per-pass kernel time on stderr (needs pcc_set_timing)
     for (;;) {
         double sums[16]; int64_t cnt = 0;
         PCC_TRY(pcc_icp_step(idx, cur, ns, sizeof(float4), apply, sums, &cnt, nullptr, nullptr, PCC_DEVICE, s));
+        idx->reuse_order_n = ns;                                  // later passes keep this pass's processing order (no key sort)
         if (trace) fprintf(stderr, "[pcc icp] pass %d: %.2f ms, %lld correspondences, mse %.3e\n", it, idx->last_ms, (long long)cnt, cnt ? sums[15] / (double)cnt : 0.0);
         if (cnt < 3) { conv = 0; break; }                        // "Not enough correspondences found"
         PCC_TRY(pcc_umeyama_from_sums(sums, cnt, Tstep));
@@ -267,7 +270,7 @@ int pcc_icp_align(pcc_index *idx, const void *src, int64_t ns, int stride_bytes,
         if (std::fabs(mse - prev_mse) < 1e-12) { conv = 1; break; }   // CONVERGENCE_CRITERIA_ABS_MSE
         prev_mse = mse;
     }
-    // getFitnessScore: ORIGINAL source moved by the final transform, mean 1-NN squared distance
+    // getFitnessScore: ORIGINAL source moved by the final transform, mean 1-NN squared distance (still the same rows, near their last position)
     if (ns > 0) {
         PCC_CUDA(cudaMemcpyAsync(d_T, Tfinal, 64, cudaMemcpyHostToDevice, s));
         xform_kernel<<<nblocks(ns, 256), 256, 0, s>>>(raw, stride_bytes, ns, d_T, cur); PCC_LAUNCHED();

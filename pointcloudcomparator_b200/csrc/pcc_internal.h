@@ -66,6 +66,7 @@ struct pcc_index {
     bool occ_valid = false;
     // scratch (grow-only, reused by every call on this index; calls on one index are serialised by the caller per stream)
     pcc::Buf raw, stage4, cellrank, qbuf, qkeys, qkeys2, qperm, qperm2, cub_tmp, out_i, out_f, out_l, keys64, keys64b, misc, parent, inv_pos, sel_params, icp_prior;
+    int64_t reuse_order_n = -1;  // pcc_icp_align: the processing order of the previous pass is kept for this many rows (points move by millimetres between passes; the order only matters for locality)
     int64_t icp_prior_n = -1;  // rows of icp_prior that hold sorted positions into the CURRENT grid (-1: none; reset by pcc_build / pcc_adopt)
     bool inv_valid = false;   // inv_pos (original row -> sorted position) is built lazily by the consumers that need it
     void *h_pinned = nullptr;  // 4 KiB pinned scratch for scalar read-backs
