@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(128) knn_fixup_kernel(Grid g, QueryView v, int
 #ifndef PCC_MB32
 #define PCC_MB32 5
 #endif
+constexpr int64_t kSmallBatch = 1024, kSmallBatchBigK = 64;   // measured: k = 16 28 us (1 query) / 56 us (1023) vs 78 us staged; k = 50 heap 55 us (1 query) but 300 us at 512 vs 260 us selection
 constexpr int kRingMaxR = 3;      // widest block knn_rings_kernel settles; beyond that a query is "wide" (knn_wide_kernel)
 template <int K> struct FastCfg { static constexpr int threads = 128, log_slots = K <= 16 ? PCC_LOG16 : PCC_LOG32, min_blocks = K <= 16 ? PCC_MB16 : PCC_MB32; };
 template <int K>
@@ -938,7 +939,11 @@ static int knn_impl(pcc_index *idx, const void *q, int64_t nq, int stride_bytes,
     const int vec4 = ((((uintptr_t)oi) | ((uintptr_t)od)) & 15) == 0 && (k % 4 == 0);
     KernelTimer timer(idx, s);
     if (qs.nq > 0) {
-        static const bool exact_only = getenv("PCC_EXACT_ONLY") != nullptr;     // debugging aid: force the ring-expansion path
+        // A small batch (the per-point calls of a PCL consumer that only swapped its tree, INTEGRATION.md level 1) is all launch
+        // latency: it takes the single-kernel exact path instead of the seven launches of the staged one (k <= 32), or the
+        // heap kernel instead of the selection path with its two read-backs (k > 32).
+        static const bool exact_env = getenv("PCC_EXACT_ONLY") != nullptr;      // debugging aid: force the ring-expansion path
+        const bool exact_only = exact_env || v.nq < (k <= 32 ? kSmallBatch : kSmallBatchBigK);
         static const bool want_stats = getenv("PCC_STATS") != nullptr;
         // warp-owns-a-cell TMA variant: opt-in (PCC_CELL_KERNEL=1).  Measured on B200 it is exact but 1.6-2.8x slower than the
         // per-thread walk even at 80 queries per cell (profiles/r1/cell_kernel_probe.jsonl), so it is never chosen automatically.
