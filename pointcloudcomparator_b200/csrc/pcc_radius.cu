@@ -189,7 +189,10 @@ __global__ void __launch_bounds__(kRowSortWarps * 32) sort_rows_kernel(const int
 // and the consumer takes the first k keys of each row: exact, canonical (d2, index) order.
 constexpr int kSelBuckets = 64;
 struct SelParam { float scale; int bucket; int R; int pad; };
-__global__ void __launch_bounds__(128) select_bound_kernel(Grid g, QueryView v, int k, int64_t *__restrict__ counts, SelParam *__restrict__ params) {
+#ifndef PCC_SELB
+#define PCC_SELB 6          // measured: 116 registers -> 80, k = 50 2.86 -> 2.70 ms, k = 100 5.27 -> 5.01 ms (2 M queries)
+#endif
+__global__ void __launch_bounds__(128, PCC_SELB) select_bound_kernel(Grid g, QueryView v, int k, int64_t *__restrict__ counts, SelParam *__restrict__ params) {
     __shared__ uint32_t hist_all[kSelBuckets * 128];
     uint32_t *hist = hist_all + threadIdx.x;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
