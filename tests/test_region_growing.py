@@ -63,3 +63,20 @@ def test_region_growing_pipeline_on_gpu_tables():
     for c in range(min(nc, 5)):
         m = normals[lab == c, :3]
         assert (np.abs(m @ m[0]) > 0.7).mean() > 0.95
+
+
+def test_region_growing_known_answer_two_perpendicular_planes():
+    """Hand-derived answer: a floor (normal +z) and a wall (normal +x) meeting in an edge, exact normals, zero curvature.
+    The 3-degree smoothness test never lets a region cross the edge, every point has in-plane neighbours, so both
+    restatements must return exactly the two planes, the floor (lowest indices, first seed) as cluster 0."""
+    g = np.arange(40, dtype=np.float32) * np.float32(0.05)
+    floor = np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2)
+    pts = np.concatenate([np.c_[floor, np.zeros(len(floor))], np.c_[np.zeros(len(floor)), floor[:, 0], floor[:, 1] + 0.05]]).astype(np.float32)
+    normals = np.zeros((len(pts), 4), np.float32)
+    normals[: len(floor), 2] = 1.0
+    normals[len(floor):, 0] = 1.0
+    nbr, _, _ = oracle.KdTree(pts).knn(pts, 12)
+    for fn in (region_growing, oracle.region_growing):
+        lab, nc = fn(nbr, normals, 3.0 / 180 * np.pi, 1.0, 50, 100000)
+        assert nc == 2
+        assert (lab[: len(floor)] == 0).all() and (lab[len(floor):] == 1).all()
