@@ -285,6 +285,7 @@ int pcc_build(pcc_index *idx, const void *pts, int64_t n, int stride_bytes, cons
     idx->inv_valid = false;
     idx->occ_valid = false;
     idx->icp_prior_n = -1;
+    ++idx->grid_gen;
     const int64_t m = indices ? n_idx : n;
     idx->n_input = n;                 // labels / self-query rows are addressed by ORIGINAL row number
     idx->n_indexed = 0;
@@ -427,6 +428,7 @@ int pcc_adopt(pcc_index *idx, const double meta[16], void *stream) {
     idx->built = true;
     idx->inv_valid = false;
     idx->icp_prior_n = -1;
+    ++idx->grid_gen;
     idx->occ_valid = false;       // the caller fills the arrays after this call: the bitmap is derived on the first query
     return PCC_OK;
 }

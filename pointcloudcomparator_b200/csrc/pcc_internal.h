@@ -65,7 +65,11 @@ struct pcc_index {
     pcc::Buf occ;             // uint32 [n_cells / 32 + 2]: one bit per cell, set when the cell holds a point (derived from cell_start)
     bool occ_valid = false;
     // scratch (grow-only, reused by every call on this index; calls on one index are serialised by the caller per stream)
-    pcc::Buf raw, stage4, cellrank, qbuf, qkeys, qkeys2, qperm, qperm2, cub_tmp, out_i, out_f, out_l, keys64, keys64b, misc, parent, inv_pos, sel_params, icp_prior;
+    pcc::Buf raw, stage4, cellrank, qbuf, qkeys, qkeys2, qperm, qperm2, cub_tmp, out_i, out_f, out_l, keys64, keys64b, misc, parent, inv_pos, sel_params, icp_prior, calib;
+    uint64_t grid_gen = 0;     // bumped by pcc_build / pcc_adopt
+    int calib_k = -1;          // k the logging-threshold table in `calib` was calibrated for (-1: none), on grid generation calib_gen of the grid owner
+    uint64_t calib_gen = 0;
+    int64_t calib_nq = 0;      // batch size of the call that last ran the block kernel (fallback monitor, see launch_knn_fast)
     int64_t reuse_order_n = -1;  // pcc_icp_align: the processing order of the previous pass is kept for this many rows (points move by millimetres between passes; the order only matters for locality)
     int64_t icp_prior_n = -1;  // rows of icp_prior that hold sorted positions into the CURRENT grid (-1: none; reset by pcc_build / pcc_adopt)
     bool inv_valid = false;   // inv_pos (original row -> sorted position) is built lazily by the consumers that need it

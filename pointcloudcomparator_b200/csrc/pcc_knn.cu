@@ -125,6 +125,9 @@ __global__ void __launch_bounds__(128) knn_fixup_kernel(Grid g, QueryView v, int
 constexpr int64_t kSmallBatch = 1024, kSmallBatchBigK = 64;   // measured: k = 16 28 us (1 query) / 56 us (1023) vs 78 us staged; k = 50 heap 55 us (1 query) but 300 us at 512 vs 260 us selection
 constexpr int kRingMaxR = 3;      // widest block knn_rings_kernel settles; beyond that a query is "wide" (knn_wide_kernel)
 template <int K> struct FastCfg { static constexpr int threads = 128, log_slots = K <= 16 ? PCC_LOG16 : PCC_LOG32, min_blocks = K <= 16 ? PCC_MB16 : PCC_MB32; };
+}  // namespace pcc
+#include "pcc_knn_thr.cuh"
+namespace pcc {
 template <int K>
 __device__ __forceinline__ float kth_distance(const Grid &g, const QueryCell &c, float x, float y, float z, int k, RegDist<K> &list, bool &proved,
                                               uint32_t *__restrict__ slog, int &nlog, const int R0) {
@@ -868,6 +871,22 @@ static void launch_knn_cell(const Grid &g, const QueryView &v, int k, int32_t *o
     knn_fixup_kernel<K><<<148 * 4, 128, 0, s>>>(g, v, k, oi, od, vec4, fix);
     PCC_LAUNCHED();
 }
+// logging-threshold table of knn_thr_kernel for (this grid, k): calibrated from a strided sample of the batch, cached in the index
+constexpr int64_t kCalibSample = 1 << 15;
+constexpr float kCalibQuantile = 0.99f;
+template <int K>
+static int calibrate_thr(pcc_index *idx, const Grid &g, const QueryView &v, int k, cudaStream_t s) {
+    PCC_TRY(idx->calib.reserve((size_t)kCalibBuckets * kCalibBins * 4 + kCalibBuckets * 4));
+    unsigned *hist = idx->calib.as<unsigned>();
+    float *ratio = (float *)(hist + kCalibBuckets * kCalibBins);
+    PCC_CUDA(cudaMemsetAsync(hist, 0, (size_t)kCalibBuckets * kCalibBins * 4, s));
+    const int64_t stride = std::max<int64_t>(1, v.nq / kCalibSample), ns = (v.nq + stride - 1) / stride;
+    knn_calib_kernel<K><<<nblocks(ns, 128), 128, 0, s>>>(g, v, k, stride, hist);
+    PCC_LAUNCHED();
+    knn_calib_finish_kernel<<<1, kCalibBuckets, 0, s>>>(hist, ratio, kCalibQuantile);
+    PCC_LAUNCHED();
+    return PCC_OK;
+}
 template <int K>
 static int launch_knn_fast(pcc_index *idx, const Grid &g, const QueryView &v, int k, int32_t *oi, float *od, int vec4, FixList fix, cudaStream_t s) {
     size_t tmp = 0;
@@ -880,8 +899,28 @@ static int launch_knn_fast(pcc_index *idx, const Grid &g, const QueryView &v, in
     }
     cudaMemsetAsync(fix.count, 0, sizeof(unsigned), s);
     cudaMemsetAsync(fix.wide_count, 0, 2 * sizeof(unsigned), s);          // wide_count and late_count are adjacent
-    knn_fast_kernel<K><<<nblocks(v.nq, FastCfg<K>::threads), FastCfg<K>::threads, 0, s>>>(g, v, k, oi, od, vec4, fix);
-    PCC_LAUNCHED();
+    static const bool old_fast = getenv("PCC_OLD_FAST") != nullptr;       // measurement aid: the round-1 block kernel (sorted insertion + candidate log)
+    if (old_fast) {
+        knn_fast_kernel<K><<<nblocks(v.nq, FastCfg<K>::threads), FastCfg<K>::threads, 0, s>>>(g, v, k, oi, od, vec4, fix);
+        PCC_LAUNCHED();
+    } else {
+        // the table only steers how many candidates a query logs (the result is exact whatever it holds), so it is kept
+        // across calls; it is re-made when the previous call sent more than 4 % of its queries to the exact path
+        // (the count is read back without a sync, so it is at worst one call late)
+        const pcc_index *owner = idx->grid_owner ? idx->grid_owner : idx;
+        unsigned *h_fb = (unsigned *)((char *)idx->h_pinned + 2048);
+        if (idx->calib_k == k && idx->calib_gen == owner->grid_gen && idx->calib_nq > 0 && (double)h_fb[0] > 0.04 * (double)idx->calib_nq) idx->calib_k = -1;
+        if (idx->calib_k != k || idx->calib_gen != owner->grid_gen) {
+            PCC_TRY(calibrate_thr<K>(idx, g, v, k, s));
+            idx->calib_k = k; idx->calib_gen = owner->grid_gen;
+        }
+        const float *ratio = (const float *)(idx->calib.as<unsigned>() + kCalibBuckets * kCalibBins);
+        PCC_CUDA(cudaFuncSetAttribute(knn_thr_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThrCfg<K>::smem));
+        knn_thr_kernel<K><<<nblocks(v.nq, ThrCfg<K>::threads), ThrCfg<K>::threads, ThrCfg<K>::smem, s>>>(g, v, k, oi, od, vec4, fix, ratio);
+        PCC_LAUNCHED();
+        h_fb[0] = 0; idx->calib_nq = v.nq;
+        PCC_CUDA(cudaMemcpyAsync(h_fb, fix.count, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    }
     // fork: the wide queries (and a short tied list) on the aux stream, beside the compaction + ring pass on `s`
     PCC_CUDA(cudaEventRecord(idx->ev_fork, s));
     PCC_CUDA(cudaStreamWaitEvent(idx->aux_stream, idx->ev_fork, 0));

@@ -1,0 +1,305 @@
+// pcc_knn_thr.cuh -- single-walk threshold selection for 2 <= k <= 32: the block kernel of pcc_knn (round 2).
+//
+// Why (profiles/r1/knn16_v8_sass_hist.txt): the round-1 block kernel kept the K smallest distances sorted in registers while it
+// walked the 3x3x3 block; the guarded min/max sweep of that list was 34 % of all issued instructions and ran whenever ANY
+// lane of the warp had something to insert (79 sweeps per warp for ~30 insertions per lane, 14 of 32 lanes active).
+//
+// Here nothing is kept sorted during the walk.  A candidate is LOGGED (its fp32 d2 and its position, 8 bytes, slot-major
+// shared memory) when d2 <= tau, with
+//        tau = dmin + T,      dmin = smallest d2 seen so far (one FMNMX per candidate),
+//        T   = ratio[M] * k / M * cell^2,      M = population of the 3x3x3 block (known from the 9 run bounds before the walk).
+// (k-th d2) - (1st d2) is what the local density predicts: for a query at height h over a surface of density rho,
+// d2_j = h^2 + j / (pi rho), so the difference does not depend on h, while d2_k itself varies by 8x at a given M when the
+// queries carry 1 cm of noise (measured on the headline workload: a threshold predicted from M alone needs 40 logged
+// candidates for 95 % coverage; dmin + T needs 25 for 98 %).  `ratio` is a 64-entry table indexed by M / 4, calibrated on
+// the device from a sample of the batch by knn_calib_kernel (quantile of (d2_k - d2_1) * M / k, exact search) and cached in
+// the index; it only steers how much is logged -- the result is exact whatever it holds:
+//   * tau only shrinks, so every candidate with d2 <= final tau is in the log;
+//   * after the walk the K-wide sorting network below selects the k smallest logged keys; if the k-th of them has
+//     d2 <= final tau the k smallest of the LOG are the k smallest of the BLOCK (every unlogged candidate is > final tau);
+//   * otherwise (too tight a table: ~1 %), or when the log overflowed, or on a tie the 32-bit keys cannot order (below), the
+//     query goes to the exact per-thread kernel (knn_fixup_kernel / knn_wide_kernel), as ties did in round 1.
+// Selection: the network sorts 32-bit keys = (d2 bits << 1, low bits replaced by the log slot): the payload rides along for
+// free with two VIMNMX per compare-exchange and no 64-bit compares.  Dropping the low 6 (7) mantissa bits cannot misorder two
+// candidates whose keys differ by >= 2^6 (2^7); adjacent keys closer than that (0.1 % of the queries; every query of a lattice
+// cloud) are "ties" and take the exact path.  The smallest dropped key is tracked so the k-th / (k+1)-th boundary is checked too.
+// The ring / wide passes behind this kernel are unchanged: it produces the same row + tau + proved flag as knn_fast_kernel.
+#pragma once
+#include <utility>
+
+#include "pcc_device.cuh"
+
+namespace pcc {
+
+#ifndef PCC_THR_SLOTS8
+#define PCC_THR_SLOTS8 32
+#endif
+#ifndef PCC_THR_SLOTS16
+#define PCC_THR_SLOTS16 48
+#endif
+#ifndef PCC_THR_SLOTS32
+#define PCC_THR_SLOTS32 96
+#endif
+#ifndef PCC_THR_MB8
+#define PCC_THR_MB8 6
+#endif
+#ifndef PCC_THR_MB16
+#define PCC_THR_MB16 4
+#endif
+#ifndef PCC_THR_MB32
+#define PCC_THR_MB32 4
+#endif
+template <int K> struct ThrCfg {
+    static constexpr int B = K <= 16 ? 16 : 32;                                          // width of the sorting network
+    static constexpr int slots = K <= 8 ? PCC_THR_SLOTS8 : (K <= 16 ? PCC_THR_SLOTS16 : PCC_THR_SLOTS32);
+    static constexpr int slot_bits = slots <= 64 ? 6 : 7;
+    static constexpr int threads = K <= 16 ? 128 : 64;
+    static constexpr int min_blocks = K <= 8 ? PCC_THR_MB8 : (K <= 16 ? PCC_THR_MB16 : PCC_THR_MB32);
+    static constexpr size_t smem = (size_t)slots * threads * sizeof(uint2);
+    static_assert(slots % B == 0, "log slots must be a multiple of the network width");
+};
+constexpr int kCalibBuckets = 64, kCalibBins = 64;
+constexpr float kCalibBinsPerOctave = 8.f;
+
+// for (I = 0; I < N; ++I) f(integral_constant<I>) with the unrolling guaranteed (a "#pragma unroll" loop over a register array
+// that also holds loads was re-rolled by the compiler, which put the array in local memory)
+template <class F, int... I> __device__ __forceinline__ void static_for_impl(F &&f, std::integer_sequence<int, I...>) { (f(std::integral_constant<int, I>{}), ...); }
+template <int N, class F> __device__ __forceinline__ void static_for(F &&f) { static_for_impl(f, std::make_integer_sequence<int, N>{}); }
+__device__ __forceinline__ void ce_u32(uint32_t &a, uint32_t &b) { const uint32_t lo = min(a, b), hi = max(a, b); a = lo; b = hi; }
+// Batcher's odd-even merge sort as a compile-time network (63 compare-exchanges for 16 keys, 191 for 32).  The pair list is
+// built by a constexpr constructor and applied through an index pack, so every array index is a literal and the keys stay in registers.
+template <int N> struct OemNet {
+    int a[N * 8], b[N * 8], n;
+    constexpr OemNet() : a(), b(), n(0) {
+        for (int p = 1; p < N; p <<= 1)
+            for (int k = p; k >= 1; k >>= 1)
+                for (int j = k % p; j <= N - 1 - k; j += 2 * k)
+                    for (int i = 0; i < k; ++i)
+                        if (i + j + k < N && (i + j) / (2 * p) == (i + j + k) / (2 * p)) { a[n] = i + j; b[n] = i + j + k; ++n; }
+    }
+};
+template <int N, int... I>
+__device__ __forceinline__ void oem_apply_u32(uint32_t (&v)[N], std::integer_sequence<int, I...>) {
+    constexpr OemNet<N> net{};
+    (ce_u32(v[net.a[I]], v[net.b[I]]), ...);
+}
+template <int N>
+__device__ __forceinline__ void oem_sort_u32(uint32_t (&v)[N]) {
+    constexpr OemNet<N> net{};
+    oem_apply_u32<N>(v, std::make_integer_sequence<int, net.n>{});
+}
+// half-cleaner stages that sort a bitonic sequence of N keys
+template <int N> struct BitonicMergeNet {
+    int a[N * 8], b[N * 8], n;
+    constexpr BitonicMergeNet() : a(), b(), n(0) {
+        for (int j = N >> 1; j > 0; j >>= 1)
+            for (int i = 0; i < N; ++i)
+                if ((i ^ j) > i) { a[n] = i; b[n] = i ^ j; ++n; }
+    }
+};
+template <int N, int... I>
+__device__ __forceinline__ void bitonic_merge_apply_u32(uint32_t (&v)[N], std::integer_sequence<int, I...>) {
+    constexpr BitonicMergeNet<N> net{};
+    (ce_u32(v[net.a[I]], v[net.b[I]]), ...);
+}
+// best (ascending) and blk (ascending) -> best = the N smallest of both, ascending; dropmin = smallest key that fell out
+template <int N>
+__device__ __forceinline__ void merge_prune_u32(uint32_t (&best)[N], const uint32_t (&blk)[N], uint32_t &dropmin) {
+    static_for<N>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        const uint32_t a = best[i], b = blk[N - 1 - i];
+        best[i] = min(a, b);                              // bitonic sequence holding the N smallest
+        dropmin = min(dropmin, max(a, b));
+    });
+    constexpr BitonicMergeNet<N> net{};
+    bitonic_merge_apply_u32<N>(best, std::make_integer_sequence<int, net.n>{});
+}
+
+// ---- calibration: exact search over the block for a strided sample of the batch -> histogram of (d2_k - d2_1) * M / k ----
+template <int K>
+__global__ void __launch_bounds__(128) knn_calib_kernel(Grid g, QueryView v, int k, int64_t stride, unsigned *__restrict__ hist) {
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * stride;
+    float x, y, z; int64_t row; bool empty;
+    if (!load_query(g, v, t, x, y, z, row, empty)) return;
+    const QueryCell c = locate(g, x, y, z);
+    RegDist<K> list; list.init();
+    uint32_t M = 0;
+    scan_shell(g, c, -1, 1, [&](uint32_t, float4 p) { list.offer(dist2(x, y, z, p.x, p.y, p.z)); ++M; });
+    const float kth = (k == K) ? list.d[K - 1] : list.at(k - 1);
+    if (kth == CUDART_INF_F) return;
+    const float ratio = (kth - list.d[0]) * g.inv_cell * g.inv_cell * (float)M / (float)k;
+    const int bin = min(max((int)floorf(log2f(fmaxf(ratio, 1e-6f)) * kCalibBinsPerOctave) + kCalibBins / 2, 0), kCalibBins - 1);
+    atomicAdd(hist + min(M >> 2, (uint32_t)kCalibBuckets - 1u) * kCalibBins + bin, 1u);
+}
+// one thread per M-bucket: upper edge of the bin that holds the `quant` quantile (a sparse bucket takes the quantile of all samples)
+__global__ void knn_calib_finish_kernel(const unsigned *__restrict__ hist, float *__restrict__ ratio, float quant) {
+    __shared__ unsigned all[kCalibBins];
+    __shared__ float all_r;
+    const int b = threadIdx.x;
+    unsigned s = 0;
+    for (int i = 0; i < kCalibBuckets; ++i) s += hist[i * kCalibBins + b];
+    all[b] = s;
+    __syncthreads();
+    if (b == 0) {
+        unsigned tot = 0; for (int j = 0; j < kCalibBins; ++j) tot += all[j];
+        float r = 8.f;                                    // no sample at all: a loose default (the exact path catches the rest)
+        if (tot) { unsigned cum = 0; int j = 0; for (; j < kCalibBins; ++j) { cum += all[j]; if ((float)cum >= quant * (float)tot) break; } r = exp2f((float)(min(j, kCalibBins - 1) + 1 - kCalibBins / 2) / kCalibBinsPerOctave); }
+        all_r = r;
+    }
+    __syncthreads();
+    unsigned tot = 0; for (int j = 0; j < kCalibBins; ++j) tot += hist[b * kCalibBins + j];
+    float r = all_r;
+    if (tot >= 64) { unsigned cum = 0; int j = 0; for (; j < kCalibBins; ++j) { cum += hist[b * kCalibBins + j]; if ((float)cum >= quant * (float)tot) break; } r = exp2f((float)(min(j, kCalibBins - 1) + 1 - kCalibBins / 2) / kCalibBinsPerOctave); }
+    ratio[b] = r;
+}
+
+// One contiguous run of the walk, four candidates per step, branch-free: every candidate is STORED at the write address and
+// the address only advances when the candidate passed (a later candidate overwrites a rejected one).  tau is refreshed once per
+// step (a stale tau within a step only logs a little more).  The write address is clamped once per step to `cap`, which
+// leaves four sacrificial slots behind it: an address AT cap after the walk means the log overflowed.
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory"); }
+// wa += STRIDE when d <= tau (one FSETP + one predicated IADD; the C form compiled to an add plus a predicated copy)
+template <uint32_t STRIDE> __device__ __forceinline__ void advance_if_le(uint32_t &wa, float d, float tau) {
+    asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.u32 %0, %0, %3;\n\t}" : "+r"(wa) : "f"(d), "f"(tau), "n"(STRIDE));
+}
+template <uint32_t STRIDE> __device__ __forceinline__ void advance_if_le_and(uint32_t &wa, float d, float tau, bool ok) {
+    asm("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %4, 0;\n\tsetp.le.and.f32 p, %1, %2, q;\n\t@p add.u32 %0, %0, %3;\n\t}" : "+r"(wa) : "f"(d), "f"(tau), "n"(STRIDE), "r"((uint32_t)ok));
+}
+template <uint32_t STRIDE>
+__device__ __forceinline__ void thr_walk_run(const Grid &g, uint32_t j, const uint32_t e, const float x, const float y, const float z, const float T,
+                                             float &dmin, float &tau, uint32_t &wa, const uint32_t cap) {
+    for (; j + 4 <= e; j += 4) {
+        const float4 p0 = __ldg(g.pts + j), p1 = __ldg(g.pts + j + 1), p2 = __ldg(g.pts + j + 2), p3 = __ldg(g.pts + j + 3);
+        const float d0 = dist2(x, y, z, p0.x, p0.y, p0.z), d1 = dist2(x, y, z, p1.x, p1.y, p1.z), d2 = dist2(x, y, z, p2.x, p2.y, p2.z), d3 = dist2(x, y, z, p3.x, p3.y, p3.z);
+        sts_v2(wa, __float_as_uint(d0), j); advance_if_le<STRIDE>(wa, d0, tau);
+        sts_v2(wa, __float_as_uint(d1), j + 1); advance_if_le<STRIDE>(wa, d1, tau);
+        sts_v2(wa, __float_as_uint(d2), j + 2); advance_if_le<STRIDE>(wa, d2, tau);
+        sts_v2(wa, __float_as_uint(d3), j + 3); advance_if_le<STRIDE>(wa, d3, tau);
+        dmin = fminf(fminf(dmin, fminf(d0, d1)), fminf(d2, d3)); tau = dmin + T;
+        wa = min(wa, cap);
+    }
+    if (j < e) {                                          // 1..3 left: the loads are clamped to the run, the extra lanes never advance
+        const float4 p0 = __ldg(g.pts + j), p1 = __ldg(g.pts + min(j + 1, e - 1)), p2 = __ldg(g.pts + min(j + 2, e - 1));
+        const float d0 = dist2(x, y, z, p0.x, p0.y, p0.z), d1 = dist2(x, y, z, p1.x, p1.y, p1.z), d2 = dist2(x, y, z, p2.x, p2.y, p2.z);
+        sts_v2(wa, __float_as_uint(d0), j); advance_if_le<STRIDE>(wa, d0, tau);
+        sts_v2(wa, __float_as_uint(d1), j + 1); advance_if_le_and<STRIDE>(wa, d1, tau, j + 1 < e);
+        sts_v2(wa, __float_as_uint(d2), j + 2); advance_if_le_and<STRIDE>(wa, d2, tau, j + 2 < e);
+        dmin = fminf(fminf(dmin, d0), fminf(d1, d2)); tau = dmin + T;
+        wa = min(wa, cap);
+    }
+}
+
+// ---- the block kernel ----
+template <int K>
+__device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, const int64_t t, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4,
+                                             const FixList &fix, const float *__restrict__ ratio, uint2 *__restrict__ slog) {
+    constexpr int TH = ThrCfg<K>::threads, SLOTS = ThrCfg<K>::slots, B = ThrCfg<K>::B;
+    constexpr uint32_t SMASK = (1u << ThrCfg<K>::slot_bits) - 1u;
+    float x, y, z; int64_t row; bool empty;
+    const bool live = load_query(g, v, t, x, y, z, row, empty);
+    if (!live) {
+        if (t < v.nq) fix.ring_flag[t] = 0;
+        if (empty) { nkey_t e[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) e[j] = PCC_EMPTY_KEY;
+            write_row<K>(e, k, out_idx + row * k, out_d2 + row * k, vec4); }
+        return;
+    }
+    const QueryCell c = locate(g, x, y, z);
+    // the 9 run bounds of the block: its population M, and a first bound for dmin (the middle point of the query's own row)
+    uint32_t M = 0, s0 = 0, e0 = 0;
+    {
+        const int xa = max(c.cx - 1, 0), xb = min(c.cx + 1, g.nx - 1);
+        uint32_t rs[9], re[9];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            const int zz = c.cz + centre_out(r / 3), yy = c.cy + centre_out(r % 3);
+            rs[r] = re[r] = 0;
+            if (zz >= 0 && zz < g.nz && yy >= 0 && yy < g.ny) {
+                const uint32_t *rowp = g.cell_start + ((size_t)zz * g.ny + yy) * g.nx;
+                rs[r] = __ldg(rowp + xa); re[r] = __ldg(rowp + xb + 1);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 9; ++r) M += re[r] - rs[r];
+        s0 = rs[0]; e0 = re[0];
+    }
+    if (M < (uint32_t)k) {                                // fewer than k points in the block: a wide query (no walk)
+        fix.ring_flag[t] = 0;
+        if (fix.stats) { atomicAdd(fix.stats + 0, 1ull); atomicAdd(fix.stats + 4, 1ull); }
+        push_list(fix.wide_list, fix.wide_count, (uint32_t)t);
+        return;
+    }
+    const float T = __ldg(ratio + min(M >> 2, (uint32_t)kCalibBuckets - 1u)) * (float)k / (float)M * (g.cell * g.cell);
+    float dmin = CUDART_INF_F;
+    if (e0 > s0) { const float4 p = __ldg(g.pts + ((s0 + e0) >> 1)); dmin = dist2(x, y, z, p.x, p.y, p.z); }
+    float tau = dmin + T;
+    // the walk: rows centre-out, each clipped to the ball of the current tau (bounds of row i+1 fetched before row i is walked)
+    constexpr uint32_t STRIDE = (uint32_t)TH * (uint32_t)sizeof(uint2);
+    const uint32_t wa0 = (uint32_t)__cvta_generic_to_shared(slog), cap = wa0 + (uint32_t)(SLOTS - 4) * STRIDE;
+    uint32_t wa = wa0;
+    {
+        int az = 0, ay = 0;
+        RowRuns nxt = row_runs(g, c, -1, 1, to_cell_units(g, tau), 0, 0);
+        for (;;) {
+            const RowRuns cur = nxt;
+            if (++ay == 3) { ay = 0; ++az; }
+            const bool more = az < 3;
+            if (more) nxt = row_runs(g, c, -1, 1, to_cell_units(g, tau), az, ay);
+            thr_walk_run<STRIDE>(g, cur.j1, cur.e1, x, y, z, T, dmin, tau, wa, cap);
+            if (!more) break;
+        }
+    }
+    const int nlog = (int)((wa - wa0) / STRIDE);          // == SLOTS - 4: the log (may have) overflowed
+    constexpr int LOGCAP = SLOTS - 4;
+    // select: the B smallest logged keys, B keys at a time
+    const int n = nlog;
+    uint32_t best[B], dropmin = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < B; ++i) best[i] = i < n ? (((slog[i * TH].x << 1) & ~SMASK) | (uint32_t)i) : 0xFFFFFFFFu;
+    oem_sort_u32<B>(best);
+    for (int b0 = B; b0 < n; b0 += B) {
+        uint32_t blk[B];
+#pragma unroll
+        for (int i = 0; i < B; ++i) blk[i] = b0 + i < n ? (((slog[(b0 + i) * TH].x << 1) & ~SMASK) | (uint32_t)(b0 + i)) : 0xFFFFFFFFu;
+        oem_sort_u32<B>(blk);
+        merge_prune_u32<B>(best, blk, dropmin);
+    }
+    // the k-th key, the smallest gap between neighbours among the first k + 1 keys
+    uint32_t kth = best[K - 1], gap = 0xFFFFFFFFu;
+    if (k != K) {                                         // best is ascending: the k-th key is the largest of the first k (written so that it cannot become a runtime index)
+        kth = 0u;
+        static_for<K - 1>([&](auto I) { constexpr int i = decltype(I)::value; kth = max(kth, i < k ? best[i] : 0u); });
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        const uint32_t nxt = i + 1 < B ? best[i + 1] : dropmin;
+        const uint32_t d = nxt - best[i];
+        gap = min(gap, i < k ? d : 0xFFFFFFFFu);
+    }
+    bool bad = nlog >= LOGCAP || kth == 0xFFFFFFFFu || gap <= SMASK;
+    float tau_k = CUDART_INF_F;
+    if (!bad) { tau_k = __uint_as_float(slog[(kth & SMASK) * TH].x); bad = !(tau_k <= tau); }
+    if (fix.stats) { atomicAdd(fix.stats + 0, 1ull); atomicAdd(fix.stats + 1, (unsigned long long)nlog); atomicAdd(fix.stats + 3, nlog >= LOGCAP ? 1ull : 0ull); atomicAdd(fix.stats + 5, bad ? 1ull : 0ull); atomicAdd(fix.stats + 6, (unsigned long long)M); }
+    if (bad) { fix.ring_flag[t] = 0; push_list(fix.list, fix.count, (uint32_t)t); return; }
+    const float cov = covered_d2(g, c, 1);
+    const bool proved = cov == CUDART_INF_F || tau_k < cov;
+    const bool wide = !proved && next_ring(g, 1, tau_k) > kRingMaxR;
+    if (fix.stats) atomicAdd(fix.stats + 4, proved ? 0ull : 1ull);
+    fix.ring_flag[t] = (!proved && !wide) ? 1 : 0;
+    if (wide) { push_list(fix.wide_list, fix.wide_count, (uint32_t)t); return; }
+    nkey_t e[K];
+    static_for<K>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        e[j] = PCC_EMPTY_KEY;
+        if (j < k) { const uint2 le = slog[(best[j] & SMASK) * TH]; e[j] = ((nkey_t)le.x << 32) | __float_as_uint(__ldg(&g.pts[le.y].w)); }
+    });
+    write_row<K>(e, k, out_idx + row * k, out_d2 + row * k, vec4);
+}
+template <int K>
+__global__ void __launch_bounds__(ThrCfg<K>::threads, ThrCfg<K>::min_blocks) knn_thr_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4, FixList fix, const float *__restrict__ ratio) {
+    extern __shared__ uint2 thr_log[];
+    knn_thr_body<K>(g, v, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, k, out_idx, out_d2, vec4, fix, ratio, thr_log + threadIdx.x);
+}
+
+}  // namespace pcc
