@@ -81,7 +81,7 @@ constexpr unsigned kTiedToWide = 4096;   // a tied-query list this short is fini
 // queries the fast path could not prove exact (listed by knn_fast_kernel)
 // `ring_flag[t]` = 1 for the queries whose 3x3x3 block did not prove the k-th distance; a stream compaction turns the flags
 // into `ring_list` / `ring_count` IN PROCESSING ORDER (neighbouring lanes stay neighbours in space) for knn_rings_kernel.
-struct FixList { uint32_t *list; unsigned *count; unsigned long long *stats; uint32_t *ring_list; unsigned *ring_count; uint8_t *ring_flag; uint32_t *wide_list; unsigned *wide_count; uint32_t *late_list; unsigned *late_count; };   // stats: optional debug counters (PCC_STATS=1)
+struct FixList { uint32_t *list; unsigned *count; unsigned long long *stats; uint32_t *ring_list; unsigned *ring_count; uint8_t *ring_flag; uint32_t *wide_list; unsigned *wide_count; uint32_t *late_list; unsigned *late_count; uint32_t *retry_list; unsigned *retry_count; };   // stats: optional debug counters (PCC_STATS=1)
 // append `value` to a device list, one atomic per warp
 __device__ __forceinline__ void push_list(uint32_t *list, unsigned *count, uint32_t value) {
     const unsigned mask = __activemask();
@@ -898,8 +898,9 @@ static int launch_knn_fast(pcc_index *idx, const Grid &g, const QueryView &v, in
         PCC_CUDA(cudaEventCreateWithFlags(&idx->ev_join, cudaEventDisableTiming));
     }
     cudaMemsetAsync(fix.count, 0, sizeof(unsigned), s);
-    cudaMemsetAsync(fix.wide_count, 0, 2 * sizeof(unsigned), s);          // wide_count and late_count are adjacent
-    static const bool old_fast = getenv("PCC_OLD_FAST") != nullptr;       // measurement aid: the round-1 block kernel (sorted insertion + candidate log)
+    cudaMemsetAsync(fix.wide_count, 0, 3 * sizeof(unsigned), s);          // wide_count, late_count and retry_count are adjacent
+    static const bool old_fast_env = getenv("PCC_OLD_FAST") != nullptr;   // measurement aid: the round-1 block kernel (sorted insertion + candidate log)
+    const bool old_fast = old_fast_env || v.nq >= (1ll << 31);             // the retry list keeps a flag bit beside the query number
     if (old_fast) {
         knn_fast_kernel<K><<<nblocks(v.nq, FastCfg<K>::threads), FastCfg<K>::threads, 0, s>>>(g, v, k, oi, od, vec4, fix);
         PCC_LAUNCHED();
@@ -915,11 +916,29 @@ static int launch_knn_fast(pcc_index *idx, const Grid &g, const QueryView &v, in
             idx->calib_k = k; idx->calib_gen = owner->grid_gen;
         }
         const float *ratio = (const float *)(idx->calib.as<unsigned>() + kCalibBuckets * kCalibBins);
-        PCC_CUDA(cudaFuncSetAttribute(knn_thr_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThrCfg<K>::smem));
-        knn_thr_kernel<K><<<nblocks(v.nq, ThrCfg<K>::threads), ThrCfg<K>::threads, ThrCfg<K>::smem, s>>>(g, v, k, oi, od, vec4, fix, ratio);
-        PCC_LAUNCHED();
+        // shared-memory carve-out: the log competes with L1 for the same 228 KB (measured sweep in DESIGN.md); PCC_THR_CARVEOUT = percent
+        static const int carve = getenv("PCC_THR_CARVEOUT") ? atoi(getenv("PCC_THR_CARVEOUT")) : -1;
+        if (carve >= 0) {
+            PCC_CUDA(cudaFuncSetAttribute(knn_thr_kernel<K, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            PCC_CUDA(cudaFuncSetAttribute(knn_thr_kernel<K, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        }
+        PCC_CUDA(cudaFuncSetAttribute(knn_thr_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThrCfg<K>::smem));
+        PCC_CUDA(cudaFuncSetAttribute(knn_thr_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThrCfg<K>::smem));
+        PCC_CUDA(cudaFuncSetAttribute(knn_thr_retry_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThrCfg<K>::smem));
+        PCC_CUDA(cudaFuncSetAttribute(knn_thr_retry_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThrCfg<K>::smem));
+        if (k == K) {
+            knn_thr_kernel<K, true><<<nblocks(v.nq, ThrCfg<K>::threads), ThrCfg<K>::threads, ThrCfg<K>::smem, s>>>(g, v, k, oi, od, vec4, fix, ratio);
+            PCC_LAUNCHED();
+            knn_thr_retry_kernel<K, true><<<148 * 4, ThrCfg<K>::threads, ThrCfg<K>::smem, s>>>(g, v, k, oi, od, vec4, fix, ratio);
+            PCC_LAUNCHED();
+        } else {
+            knn_thr_kernel<K, false><<<nblocks(v.nq, ThrCfg<K>::threads), ThrCfg<K>::threads, ThrCfg<K>::smem, s>>>(g, v, k, oi, od, vec4, fix, ratio);
+            PCC_LAUNCHED();
+            knn_thr_retry_kernel<K, false><<<148 * 4, ThrCfg<K>::threads, ThrCfg<K>::smem, s>>>(g, v, k, oi, od, vec4, fix, ratio);
+            PCC_LAUNCHED();
+        }
         h_fb[0] = 0; idx->calib_nq = v.nq;
-        PCC_CUDA(cudaMemcpyAsync(h_fb, fix.count, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+        PCC_CUDA(cudaMemcpyAsync(h_fb, fix.retry_count, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     }
     // fork: the wide queries (and a short tied list) on the aux stream, beside the compaction + ring pass on `s`
     PCC_CUDA(cudaEventRecord(idx->ev_fork, s));
@@ -988,11 +1007,11 @@ static int knn_impl(pcc_index *idx, const void *q, int64_t nq, int stride_bytes,
         // per-thread walk even at 80 queries per cell (profiles/r1/cell_kernel_probe.jsonl), so it is never chosen automatically.
         const char *cell_env = getenv("PCC_CELL_KERNEL");
         const bool use_cell = cell_env && atoi(cell_env) != 0;
-        FixList fix{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        FixList fix{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
         if (k > 1 && k <= 32 && !exact_only) {
-            PCC_TRY(idx->misc.reserve((size_t)v.nq * 17 + 256));
-            fix.count = idx->misc.as<unsigned>(); fix.ring_count = fix.count + 1; fix.wide_count = fix.count + 30; fix.late_count = fix.count + 31;
-            fix.list = idx->misc.as<uint32_t>() + 32; fix.ring_list = fix.list + v.nq; fix.wide_list = fix.ring_list + v.nq; fix.late_list = fix.wide_list + v.nq; fix.ring_flag = (uint8_t *)(fix.late_list + v.nq);
+            PCC_TRY(idx->misc.reserve((size_t)v.nq * 21 + 512));
+            fix.count = idx->misc.as<unsigned>(); fix.ring_count = fix.count + 1; fix.wide_count = fix.count + 30; fix.late_count = fix.count + 31; fix.retry_count = fix.count + 32;
+            fix.list = idx->misc.as<uint32_t>() + 64; fix.ring_list = fix.list + v.nq; fix.wide_list = fix.ring_list + v.nq; fix.late_list = fix.wide_list + v.nq; fix.retry_list = fix.late_list + v.nq; fix.ring_flag = (uint8_t *)(fix.retry_list + v.nq);
             if (want_stats) { fix.stats = (unsigned long long *)(idx->misc.as<uint32_t>() + 2); PCC_CUDA(cudaMemsetAsync(fix.stats, 0, 112, s)); }
         }
         if (k == 1) launch_knn_reg<1>(g, v, k, oi, od, vec4, s);

@@ -17,8 +17,9 @@
 //   * tau only shrinks, so every candidate with d2 <= final tau is in the log;
 //   * after the walk the K-wide sorting network below selects the k smallest logged keys; if the k-th of them has
 //     d2 <= final tau the k smallest of the LOG are the k smallest of the BLOCK (every unlogged candidate is > final tau);
-//   * otherwise (too tight a table: ~1 %), or when the log overflowed, or on a tie the 32-bit keys cannot order (below), the
-//     query goes to the exact per-thread kernel (knn_fixup_kernel / knn_wide_kernel), as ties did in round 1.
+//   * otherwise (too tight a table: ~1 %) the query is listed and knn_thr_retry_kernel runs it again with 4 T; when the log
+//     overflowed, or on a tie the 32-bit keys cannot order (below), the retry kernel runs the exact per-thread search (64-bit
+//     keys, ring expansion) for it instead.
 // Selection: the network sorts 32-bit keys = (d2 bits << 1, low bits replaced by the log slot): the payload rides along for
 // free with two VIMNMX per compare-exchange and no 64-bit compares.  Dropping the low 6 (7) mantissa bits cannot misorder two
 // candidates whose keys differ by >= 2^6 (2^7); adjacent keys closer than that (0.1 % of the queries; every query of a lattice
@@ -32,13 +33,13 @@
 namespace pcc {
 
 #ifndef PCC_THR_SLOTS8
-#define PCC_THR_SLOTS8 32
+#define PCC_THR_SLOTS8 36
 #endif
 #ifndef PCC_THR_SLOTS16
 #define PCC_THR_SLOTS16 48
 #endif
 #ifndef PCC_THR_SLOTS32
-#define PCC_THR_SLOTS32 96
+#define PCC_THR_SLOTS32 100
 #endif
 #ifndef PCC_THR_MB8
 #define PCC_THR_MB8 6
@@ -49,14 +50,20 @@ namespace pcc {
 #ifndef PCC_THR_MB32
 #define PCC_THR_MB32 4
 #endif
+// Launch shape.  Log entry = (d2 bits, position), 8 bytes.  Measured on B200, headline workload (profiles/r2/): the kernel is
+// co-limited by issue slots (46-51 %) and the L1 data pipe (54-68 % of its wavefronts: a 16-byte load whose 32 lanes sit in ~8
+// different cells costs ~8 sector wavefronts).  A 4-byte log (position only, d2 recomputed in the selection) doubles the
+// resident warps but its recompute loads -- every lane a different address, ~20 sectors per request -- cost more wavefronts
+// than the whole walk: 2.69 ms vs 2.50 ms.  Blocks per SM (4..8), log slots (48 / 64) and the shared-memory carve-out
+// (44..100 %) moved the 4-byte variant by < 5 % (r2f_carve.log), so the shape below is simply the one without spills.
 template <int K> struct ThrCfg {
     static constexpr int B = K <= 16 ? 16 : 32;                                          // width of the sorting network
-    static constexpr int slots = K <= 8 ? PCC_THR_SLOTS8 : (K <= 16 ? PCC_THR_SLOTS16 : PCC_THR_SLOTS32);
+    static constexpr int slots = K <= 8 ? PCC_THR_SLOTS8 : (K <= 16 ? PCC_THR_SLOTS16 : PCC_THR_SLOTS32);   // the last 4 are sacrificial
     static constexpr int slot_bits = slots <= 64 ? 6 : 7;
     static constexpr int threads = K <= 16 ? 128 : 64;
     static constexpr int min_blocks = K <= 8 ? PCC_THR_MB8 : (K <= 16 ? PCC_THR_MB16 : PCC_THR_MB32);
     static constexpr size_t smem = (size_t)slots * threads * sizeof(uint2);
-    static_assert(slots % B == 0, "log slots must be a multiple of the network width");
+    static_assert(slots <= (1 << slot_bits) && slots % 4 == 0, "log slots must fit the key's slot field");
 };
 constexpr int kCalibBuckets = 64, kCalibBins = 64;
 constexpr float kCalibBinsPerOctave = 8.f;
@@ -153,10 +160,11 @@ __global__ void knn_calib_finish_kernel(const unsigned *__restrict__ hist, float
     ratio[b] = r;
 }
 
-// One contiguous run of the walk, four candidates per step, branch-free: every candidate is STORED at the write address and
-// the address only advances when the candidate passed (a later candidate overwrites a rejected one).  tau is refreshed once per
-// step (a stale tau within a step only logs a little more).  The write address is clamped once per step to `cap`, which
-// leaves four sacrificial slots behind it: an address AT cap after the walk means the log overflowed.
+// One contiguous run of the walk, four candidates per step, branch-free: every candidate's (d2, position) is STORED at the write
+// address and the address only advances when the candidate passed (a later candidate overwrites a rejected one).  tau is
+// refreshed once per step (a stale tau within a step only logs a little more).  The write address is clamped once per step to
+// `cap`, which leaves four sacrificial slots behind it: an address AT cap after the walk means the log overflowed (first pass);
+// the retry pass (COMPRESS) compresses the log instead of clamping, so nothing is ever lost there.
 __device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory"); }
 // wa += STRIDE when d <= tau (one FSETP + one predicated IADD; the C form compiled to an add plus a predicated copy)
 template <uint32_t STRIDE> __device__ __forceinline__ void advance_if_le(uint32_t &wa, float d, float tau) {
@@ -165,9 +173,30 @@ template <uint32_t STRIDE> __device__ __forceinline__ void advance_if_le(uint32_
 template <uint32_t STRIDE> __device__ __forceinline__ void advance_if_le_and(uint32_t &wa, float d, float tau, bool ok) {
     asm("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %4, 0;\n\tsetp.le.and.f32 p, %1, %2, q;\n\t@p add.u32 %0, %0, %3;\n\t}" : "+r"(wa) : "f"(d), "f"(tau), "n"(STRIDE), "r"((uint32_t)ok));
 }
-template <uint32_t STRIDE>
-__device__ __forceinline__ void thr_walk_run(const Grid &g, uint32_t j, const uint32_t e, const float x, const float y, const float z, const float T,
-                                             float &dmin, float &tau, uint32_t &wa, const uint32_t cap) {
+// The walk is bound by the latency of its point loads, not by issue (ncu, 8-byte-log version: 46 % issue slots, 3.5 of 8 stall
+// cycles per issue on the load scoreboard, L2 hit rate 49 %: the first warp to touch a cell's points pays DRAM latency, and a step of
+// 4 x 32 lane loads touches ~10 lines).  Prefetches cost no registers and no scoreboard: all nine rows go to L2 as soon as their
+// bounds are known, and row i+1 goes to L1 while row i is walked.
+#ifndef PCC_THR_PREFETCH
+#define PCC_THR_PREFETCH 3
+#endif
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// up to LINES 128-byte lines of the run [j, e) (8 points per line; a 3-cell run holds ~25 points)
+template <int LINES, bool L1>
+__device__ __forceinline__ void prefetch_run(const float4 *pts, uint32_t j, uint32_t e) {
+    if (j >= e) return;
+    const char *a = (const char *)(pts + j), *last = (const char *)(pts + (e - 1));
+#pragma unroll
+    for (int i = 0; i < LINES; ++i) {
+        const char *q = a + 128 * i;
+        if (q <= last || i == 0) { if (L1) prefetch_l1(q); else prefetch_l2(q); }
+    }
+    if (L1) prefetch_l1(last); else prefetch_l2(last);
+}
+template <uint32_t STRIDE, bool COMPRESS, class F>
+__device__ __forceinline__ void thr_walk_run(const Grid &g, uint32_t j, const uint32_t e, const float x, const float y, const float z, float &T,
+                                             float &dmin, float &tau, uint32_t &wa, const uint32_t cap, F &&on_full) {
     for (; j + 4 <= e; j += 4) {
         const float4 p0 = __ldg(g.pts + j), p1 = __ldg(g.pts + j + 1), p2 = __ldg(g.pts + j + 2), p3 = __ldg(g.pts + j + 3);
         const float d0 = dist2(x, y, z, p0.x, p0.y, p0.z), d1 = dist2(x, y, z, p1.x, p1.y, p1.z), d2 = dist2(x, y, z, p2.x, p2.y, p2.z), d3 = dist2(x, y, z, p3.x, p3.y, p3.z);
@@ -176,7 +205,8 @@ __device__ __forceinline__ void thr_walk_run(const Grid &g, uint32_t j, const ui
         sts_v2(wa, __float_as_uint(d2), j + 2); advance_if_le<STRIDE>(wa, d2, tau);
         sts_v2(wa, __float_as_uint(d3), j + 3); advance_if_le<STRIDE>(wa, d3, tau);
         dmin = fminf(fminf(dmin, fminf(d0, d1)), fminf(d2, d3)); tau = dmin + T;
-        wa = min(wa, cap);
+        if (!COMPRESS) wa = min(wa, cap);
+        else if (wa >= cap) on_full();                    // not clamped first: the entries in the sacrificial slots are real
     }
     if (j < e) {                                          // 1..3 left: the loads are clamped to the run, the extra lanes never advance
         const float4 p0 = __ldg(g.pts + j), p1 = __ldg(g.pts + min(j + 1, e - 1)), p2 = __ldg(g.pts + min(j + 2, e - 1));
@@ -185,16 +215,27 @@ __device__ __forceinline__ void thr_walk_run(const Grid &g, uint32_t j, const ui
         sts_v2(wa, __float_as_uint(d1), j + 1); advance_if_le_and<STRIDE>(wa, d1, tau, j + 1 < e);
         sts_v2(wa, __float_as_uint(d2), j + 2); advance_if_le_and<STRIDE>(wa, d2, tau, j + 2 < e);
         dmin = fminf(fminf(dmin, d0), fminf(d1, d2)); tau = dmin + T;
-        wa = min(wa, cap);
+        if (!COMPRESS) wa = min(wa, cap);
+        else if (wa >= cap) on_full();                    // not clamped first: the entries in the sacrificial slots are real
     }
 }
 
 // ---- the block kernel ----
-template <int K>
-__device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, const int64_t t, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4,
-                                             const FixList &fix, const float *__restrict__ ratio, uint2 *__restrict__ slog) {
+// FULLK: k == K (every per-element "j < k" test folds away).
+// RETRY: the second pass, over the compacted list of queries the first pass could not settle (~1 %):
+//   * table entry too tight (the k-th logged d2 is beyond the final tau): walked again with 4 T;
+//   * log overflow (a block denser than its table entry expects): walked again, and whenever the log fills up it is COMPRESSED
+//     in place -- the k-th smallest logged d2 is an upper bound of the k-th distance (every entry is a real candidate): tau
+//     drops to it, entries beyond tau are discarded and the walk goes on;
+//   * a tie the 32-bit keys cannot order: the k smallest are picked from the log with exact 64-bit (d2, index) keys.
+// Only what is still unsettled after that (more ties than the log holds) runs the exact per-thread search with ring expansion.
+constexpr float kRetryScale = 4.f;
+template <int K, bool FULLK, bool RETRY>
+__device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, const int64_t t, const int k_rt, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4,
+                                             const FixList &fix, const float *__restrict__ ratio, uint2 *__restrict__ slog, const bool loose = false) {
     constexpr int TH = ThrCfg<K>::threads, SLOTS = ThrCfg<K>::slots, B = ThrCfg<K>::B;
     constexpr uint32_t SMASK = (1u << ThrCfg<K>::slot_bits) - 1u;
+    const int k = FULLK ? K : k_rt;
     float x, y, z; int64_t row; bool empty;
     const bool live = load_query(g, v, t, x, y, z, row, empty);
     if (!live) {
@@ -221,7 +262,7 @@ __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, 
             }
         }
 #pragma unroll
-        for (int r = 0; r < 9; ++r) M += re[r] - rs[r];
+        for (int r = 0; r < 9; ++r) { M += re[r] - rs[r]; if (PCC_THR_PREFETCH & 1) prefetch_run<3, false>(g.pts, rs[r], re[r]); }
         s0 = rs[0]; e0 = re[0];
     }
     if (M < (uint32_t)k) {                                // fewer than k points in the block: a wide query (no walk)
@@ -230,14 +271,55 @@ __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, 
         push_list(fix.wide_list, fix.wide_count, (uint32_t)t);
         return;
     }
-    const float T = __ldg(ratio + min(M >> 2, (uint32_t)kCalibBuckets - 1u)) * (float)k / (float)M * (g.cell * g.cell);
+    float T = __ldg(ratio + min(M >> 2, (uint32_t)kCalibBuckets - 1u)) * (float)k / (float)M * (g.cell * g.cell) * ((RETRY && loose) ? kRetryScale : 1.f);
     float dmin = CUDART_INF_F;
     if (e0 > s0) { const float4 p = __ldg(g.pts + ((s0 + e0) >> 1)); dmin = dist2(x, y, z, p.x, p.y, p.z); }
     float tau = dmin + T;
-    // the walk: rows centre-out, each clipped to the ball of the current tau (bounds of row i+1 fetched before row i is walked)
     constexpr uint32_t STRIDE = (uint32_t)TH * (uint32_t)sizeof(uint2);
-    const uint32_t wa0 = (uint32_t)__cvta_generic_to_shared(slog), cap = wa0 + (uint32_t)(SLOTS - 4) * STRIDE;
+    constexpr int LOGCAP = SLOTS - 4;
+    const uint32_t wa0 = (uint32_t)__cvta_generic_to_shared(slog), cap = wa0 + (uint32_t)LOGCAP * STRIDE;
     uint32_t wa = wa0;
+    // select: the B smallest of the first n logged keys, B log slots at a time.  key = (d2 bits << 1, low bits = slot)
+    uint32_t best[B], dropmin;
+    auto select_log = [&](const int n) {
+        auto load_keys = [&](uint32_t (&key)[B], const int b0) {
+            static_for<B>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                key[i] = b0 + i < n ? (((slog[(b0 + i) * TH].x << 1) & ~SMASK) | (uint32_t)(b0 + i)) : 0xFFFFFFFFu;
+            });
+        };
+        dropmin = 0xFFFFFFFFu;
+        load_keys(best, 0);
+        oem_sort_u32<B>(best);
+        for (int b0 = B; b0 < n; b0 += B) {
+            uint32_t blk[B];
+            load_keys(blk, b0);
+            oem_sort_u32<B>(blk);
+            merge_prune_u32<B>(best, blk, dropmin);
+        }
+    };
+    auto kth_key = [&]() {
+        uint32_t kth = best[K - 1];
+        if (!FULLK) {                                     // best is ascending: the k-th key is the largest of the first k (written so that it cannot become a runtime index)
+            kth = 0u;
+            static_for<K - 1>([&](auto I) { constexpr int i = decltype(I)::value; kth = max(kth, i < k ? best[i] : 0u); });
+        }
+        return kth;
+    };
+    bool give_up = false;
+    auto on_full = [&]() {                                // RETRY only: compress the full log in place (see above)
+        const int nf = (int)((wa - wa0) / STRIDE);        // LOGCAP .. LOGCAP + 3 entries
+        select_log(nf);
+        const float tau_new = __uint_as_float(slog[(kth_key() & SMASK) * TH].x) * (1.f + 1.f / 32768.f);     // 2^-15 covers the key truncation
+        // The log is complete up to the CURRENT tau only (earlier entries passed looser thresholds), so tau may shrink to tau_new
+        // but never grow: constant threshold from here on if the bound is the tighter one (d2 >= 0 keeps dmin at 0).
+        if (tau_new < tau) { dmin = 0.f; T = tau_new; tau = tau_new; }
+        int m = 0;
+        for (int i = 0; i < nf; ++i) { const uint2 e = slog[i * TH]; if (__uint_as_float(e.x) <= tau) { slog[m * TH] = e; ++m; } }
+        if (m >= LOGCAP - 4) { give_up = true; m = 0; }   // more candidates inside tau than the log holds (ties)
+        wa = wa0 + (uint32_t)m * STRIDE;
+    };
+    // the walk: rows centre-out, each clipped to the ball of the current tau (bounds of row i+1 fetched before row i is walked)
     {
         int az = 0, ay = 0;
         RowRuns nxt = row_runs(g, c, -1, 1, to_cell_units(g, tau), 0, 0);
@@ -245,61 +327,84 @@ __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, 
             const RowRuns cur = nxt;
             if (++ay == 3) { ay = 0; ++az; }
             const bool more = az < 3;
-            if (more) nxt = row_runs(g, c, -1, 1, to_cell_units(g, tau), az, ay);
-            thr_walk_run<STRIDE>(g, cur.j1, cur.e1, x, y, z, T, dmin, tau, wa, cap);
+            if (more) { nxt = row_runs(g, c, -1, 1, to_cell_units(g, tau), az, ay); if (PCC_THR_PREFETCH & 2) prefetch_run<3, true>(g.pts, nxt.j1, nxt.e1); }
+            thr_walk_run<STRIDE, RETRY>(g, cur.j1, cur.e1, x, y, z, T, dmin, tau, wa, cap, on_full);
             if (!more) break;
         }
     }
-    const int nlog = (int)((wa - wa0) / STRIDE);          // == SLOTS - 4: the log (may have) overflowed
-    constexpr int LOGCAP = SLOTS - 4;
-    // select: the B smallest logged keys, B keys at a time
-    const int n = nlog;
-    uint32_t best[B], dropmin = 0xFFFFFFFFu;
-#pragma unroll
-    for (int i = 0; i < B; ++i) best[i] = i < n ? (((slog[i * TH].x << 1) & ~SMASK) | (uint32_t)i) : 0xFFFFFFFFu;
-    oem_sort_u32<B>(best);
-    for (int b0 = B; b0 < n; b0 += B) {
-        uint32_t blk[B];
-#pragma unroll
-        for (int i = 0; i < B; ++i) blk[i] = b0 + i < n ? (((slog[(b0 + i) * TH].x << 1) & ~SMASK) | (uint32_t)(b0 + i)) : 0xFFFFFFFFu;
-        oem_sort_u32<B>(blk);
-        merge_prune_u32<B>(best, blk, dropmin);
-    }
+    if (RETRY && give_up) { fix.ring_flag[t] = 0; knn_reg_body<K>(g, v, t, k, out_idx, out_d2, vec4); return; }
+    const int n = (int)((wa - wa0) / STRIDE);             // == LOGCAP: the log (may have) overflowed
+    select_log(n);
     // the k-th key, the smallest gap between neighbours among the first k + 1 keys
-    uint32_t kth = best[K - 1], gap = 0xFFFFFFFFu;
-    if (k != K) {                                         // best is ascending: the k-th key is the largest of the first k (written so that it cannot become a runtime index)
-        kth = 0u;
-        static_for<K - 1>([&](auto I) { constexpr int i = decltype(I)::value; kth = max(kth, i < k ? best[i] : 0u); });
-    }
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
+    const uint32_t kth = kth_key();
+    uint32_t gap = 0xFFFFFFFFu;
+    static_for<K>([&](auto I) {
+        constexpr int i = decltype(I)::value;
         const uint32_t nxt = i + 1 < B ? best[i + 1] : dropmin;
         const uint32_t d = nxt - best[i];
-        gap = min(gap, i < k ? d : 0xFFFFFFFFu);
-    }
-    bool bad = nlog >= LOGCAP || kth == 0xFFFFFFFFu || gap <= SMASK;
+        gap = min(gap, (FULLK || i < k) ? d : 0xFFFFFFFFu);
+    });
+    const bool overflow = n >= LOGCAP;
+    const bool tie = kth == 0xFFFFFFFFu || gap <= SMASK;
+    // exact d2 of the k-th logged candidate
     float tau_k = CUDART_INF_F;
-    if (!bad) { tau_k = __uint_as_float(slog[(kth & SMASK) * TH].x); bad = !(tau_k <= tau); }
-    if (fix.stats) { atomicAdd(fix.stats + 0, 1ull); atomicAdd(fix.stats + 1, (unsigned long long)nlog); atomicAdd(fix.stats + 3, nlog >= LOGCAP ? 1ull : 0ull); atomicAdd(fix.stats + 5, bad ? 1ull : 0ull); atomicAdd(fix.stats + 6, (unsigned long long)M); }
-    if (bad) { fix.ring_flag[t] = 0; push_list(fix.list, fix.count, (uint32_t)t); return; }
+    if (kth != 0xFFFFFFFFu) tau_k = __uint_as_float(slog[(kth & SMASK) * TH].x);
+    const bool under = !(tau_k <= tau);                    // the threshold was too tight: an unlogged candidate may be nearer than the k-th logged one
+    if (fix.stats && !RETRY) { atomicAdd(fix.stats + 0, 1ull); atomicAdd(fix.stats + 1, (unsigned long long)n); atomicAdd(fix.stats + 3, overflow ? 1ull : 0ull); atomicAdd(fix.stats + 5, (overflow || tie || under) ? 1ull : 0ull); atomicAdd(fix.stats + 6, (unsigned long long)M); }
+    if (!RETRY && (overflow || tie || under)) {           // list it for the retry pass (bit 31: 4 T)
+        fix.ring_flag[t] = 0;
+        push_list(fix.retry_list, fix.retry_count, (uint32_t)t | ((under && !overflow) ? 0x80000000u : 0u));
+        return;
+    }
+    int32_t *oi = out_idx + row * k; float *od = out_d2 + row * k;
+    if (RETRY && (overflow || tie || under)) {
+        // exact selection from the log: 64-bit (d2, index) keys, insertion-sorted.  Valid when the log is complete up to its k-th d2.
+        RegList<K> list; list.init();
+        if (!overflow) for (int i = 0; i < n; ++i) { const uint2 e = slog[i * TH]; list.offer(((nkey_t)e.x << 32) | __float_as_uint(__ldg(&g.pts[e.y].w))); }
+        const nkey_t kk = FULLK ? list.key[K - 1] : list.at(k - 1);
+        tau_k = key_d2(kk);
+        if (overflow || kk == PCC_EMPTY_KEY || !(tau_k <= tau)) { fix.ring_flag[t] = 0; knn_reg_body<K>(g, v, t, k, out_idx, out_d2, vec4); return; }
+        const float cov = covered_d2(g, c, 1);
+        const bool proved = cov == CUDART_INF_F || tau_k < cov;
+        const bool wide = !proved && next_ring(g, 1, tau_k) > kRingMaxR;
+        fix.ring_flag[t] = (!proved && !wide) ? 1 : 0;
+        if (wide) { push_list(fix.wide_list, fix.wide_count, (uint32_t)t); return; }
+        write_row<K>(list.key, k, oi, od, vec4);
+        return;
+    }
     const float cov = covered_d2(g, c, 1);
     const bool proved = cov == CUDART_INF_F || tau_k < cov;
     const bool wide = !proved && next_ring(g, 1, tau_k) > kRingMaxR;
-    if (fix.stats) atomicAdd(fix.stats + 4, proved ? 0ull : 1ull);
+    if (fix.stats && !RETRY) atomicAdd(fix.stats + 4, proved ? 0ull : 1ull);
     fix.ring_flag[t] = (!proved && !wide) ? 1 : 0;
     if (wide) { push_list(fix.wide_list, fix.wide_count, (uint32_t)t); return; }
-    nkey_t e[K];
-    static_for<K>([&](auto J) {
-        constexpr int j = decltype(J)::value;
-        e[j] = PCC_EMPTY_KEY;
-        if (j < k) { const uint2 le = slog[(best[j] & SMASK) * TH]; e[j] = ((nkey_t)le.x << 32) | __float_as_uint(__ldg(&g.pts[le.y].w)); }
+    // the row: exact d2 from the log, original index from the point's .w, four at a time
+    static_for<K / 4>([&](auto Q) {
+        constexpr int q = decltype(Q)::value * 4;
+        uint2 le[4]; int32_t id[4];
+        static_for<4>([&](auto I) { constexpr int i = decltype(I)::value; le[i] = (FULLK || q + i < k) ? slog[(best[q + i] & SMASK) * TH] : make_uint2(0u, 0u); });     // keys past k may be empty
+        static_for<4>([&](auto I) { constexpr int i = decltype(I)::value; id[i] = __float_as_int(__ldg(&g.pts[le[i].y].w)); });
+        if (FULLK && vec4) {
+            reinterpret_cast<int4 *>(oi)[q >> 2] = make_int4(id[0], id[1], id[2], id[3]);
+            reinterpret_cast<float4 *>(od)[q >> 2] = make_float4(__uint_as_float(le[0].x), __uint_as_float(le[1].x), __uint_as_float(le[2].x), __uint_as_float(le[3].x));
+        } else {
+            static_for<4>([&](auto I) { constexpr int i = decltype(I)::value; if (q + i < k) { oi[q + i] = id[i]; od[q + i] = __uint_as_float(le[i].x); } });
+        }
     });
-    write_row<K>(e, k, out_idx + row * k, out_d2 + row * k, vec4);
 }
-template <int K>
+template <int K, bool FULLK>
 __global__ void __launch_bounds__(ThrCfg<K>::threads, ThrCfg<K>::min_blocks) knn_thr_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4, FixList fix, const float *__restrict__ ratio) {
     extern __shared__ uint2 thr_log[];
-    knn_thr_body<K>(g, v, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, k, out_idx, out_d2, vec4, fix, ratio, thr_log + threadIdx.x);
+    knn_thr_body<K, FULLK, false>(g, v, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, k, out_idx, out_d2, vec4, fix, ratio, thr_log + threadIdx.x);
+}
+template <int K, bool FULLK>
+__global__ void __launch_bounds__(ThrCfg<K>::threads, 2) knn_thr_retry_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4, FixList fix, const float *__restrict__ ratio) {
+    extern __shared__ uint2 thr_log[];
+    const unsigned n = *fix.retry_count;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t e = fix.retry_list[i];
+        knn_thr_body<K, FULLK, true>(g, v, (int64_t)(e & 0x7FFFFFFFu), k, out_idx, out_d2, vec4, fix, ratio, thr_log + threadIdx.x, (e >> 31) != 0u);
+    }
 }
 
 }  // namespace pcc

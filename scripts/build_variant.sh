@@ -11,5 +11,5 @@ cp -r $root/pointcloudcomparator_b200/csrc $d/pointcloudcomparator_b200/csrc
 rm -f $d/pointcloudcomparator_b200/csrc/*.o
 ln -sfn $root/include $d/include
 make -s -C $d/pointcloudcomparator_b200/csrc -j6 EXTRA="$*" OUT=$root/_variants/$name.so
-grep -A1 "knn_fast_kernelILi16" $d/pointcloudcomparator_b200/csrc/pcc_knn.ptxas.log | grep -o "Used [0-9]* registers.*" | head -1
+grep -A2 "knn_thr_kernelILi16ELb1" $d/pointcloudcomparator_b200/csrc/pcc_knn.ptxas.log | grep -E -o "Used [0-9]* registers|[0-9]* bytes spill stores" | head -2
 rm -rf $d
