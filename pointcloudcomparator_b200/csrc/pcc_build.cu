@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include <cstring>
 #include "pcc_internal.h"
 
 namespace pcc {
@@ -240,6 +241,7 @@ int pcc_create(int device, pcc_index **out) {
     pcc_index *idx = new pcc_index();
     idx->device = device;
     PCC_CUDA(cudaMallocHost(&idx->h_pinned, 4096));
+    memset(idx->h_pinned, 0, 4096);
     PCC_CUDA(cudaEventCreate(&idx->ev0));
     PCC_CUDA(cudaEventCreate(&idx->ev1));
     *out = idx;
@@ -252,7 +254,7 @@ void pcc_destroy(pcc_index *idx) {
     if (idx->shadow) { pcc_index *sh = idx->shadow; idx->shadow = nullptr; pcc_destroy(sh); }
     for (int i = 0; i < 2; ++i) if (idx->pipe_stream[i]) cudaStreamDestroy(idx->pipe_stream[i]);
     Buf *bufs[] = {&idx->pts, &idx->cell_start, &idx->occ, &idx->raw, &idx->stage4, &idx->cellrank, &idx->qbuf, &idx->qkeys, &idx->qkeys2, &idx->qperm, &idx->qperm2,
-                   &idx->cub_tmp, &idx->out_i, &idx->out_f, &idx->out_l, &idx->keys64, &idx->keys64b, &idx->misc, &idx->parent, &idx->inv_pos, &idx->sel_params, &idx->icp_prior};
+                   &idx->cub_tmp, &idx->out_i, &idx->out_f, &idx->out_l, &idx->keys64, &idx->keys64b, &idx->misc, &idx->parent, &idx->inv_pos, &idx->sel_params, &idx->icp_prior, &idx->calib};
     for (Buf *b : bufs) b->release();
     if (idx->h_pinned) cudaFreeHost(idx->h_pinned);
     if (idx->aux_stream) cudaStreamDestroy(idx->aux_stream);

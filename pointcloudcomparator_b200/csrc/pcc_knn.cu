@@ -900,7 +900,11 @@ static int launch_knn_fast(pcc_index *idx, const Grid &g, const QueryView &v, in
     cudaMemsetAsync(fix.count, 0, sizeof(unsigned), s);
     cudaMemsetAsync(fix.wide_count, 0, 3 * sizeof(unsigned), s);          // wide_count, late_count and retry_count are adjacent
     static const bool old_fast_env = getenv("PCC_OLD_FAST") != nullptr;   // measurement aid: the round-1 block kernel (sorted insertion + candidate log)
-    const bool old_fast = old_fast_env || v.nq >= (1ll << 31);             // the retry list keeps a flag bit beside the query number
+    // Measured on B200, 10 M queries vs the 10 M-point surface cloud (profiles/r2/sweep_k_blockkernel.txt): the threshold kernel wins at
+    // K = 16 (3.50 vs 3.81 ms), ties at K = 8 (2.53 / 2.51) and loses at K = 4 (2.28 / 2.07: ~10 logged candidates do not pay for a
+    // 16-wide network) and K = 32 (10.96 / 9.17: two 32-wide networks per block of the log), so it serves 8 < k <= 16 only.
+    static const bool thr_all = getenv("PCC_THR_ALL") != nullptr;
+    const bool old_fast = old_fast_env || (K != 16 && !thr_all) || v.nq >= (1ll << 31);     // the retry list keeps a flag bit beside the query number
     if (old_fast) {
         knn_fast_kernel<K><<<nblocks(v.nq, FastCfg<K>::threads), FastCfg<K>::threads, 0, s>>>(g, v, k, oi, od, vec4, fix);
         PCC_LAUNCHED();
@@ -916,12 +920,6 @@ static int launch_knn_fast(pcc_index *idx, const Grid &g, const QueryView &v, in
             idx->calib_k = k; idx->calib_gen = owner->grid_gen;
         }
         const float *ratio = (const float *)(idx->calib.as<unsigned>() + kCalibBuckets * kCalibBins);
-        // shared-memory carve-out: the log competes with L1 for the same 228 KB (measured sweep in DESIGN.md); PCC_THR_CARVEOUT = percent
-        static const int carve = getenv("PCC_THR_CARVEOUT") ? atoi(getenv("PCC_THR_CARVEOUT")) : -1;
-        if (carve >= 0) {
-            PCC_CUDA(cudaFuncSetAttribute(knn_thr_kernel<K, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            PCC_CUDA(cudaFuncSetAttribute(knn_thr_kernel<K, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-        }
         PCC_CUDA(cudaFuncSetAttribute(knn_thr_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThrCfg<K>::smem));
         PCC_CUDA(cudaFuncSetAttribute(knn_thr_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThrCfg<K>::smem));
         PCC_CUDA(cudaFuncSetAttribute(knn_thr_retry_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThrCfg<K>::smem));

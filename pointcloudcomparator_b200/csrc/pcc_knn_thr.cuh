@@ -194,20 +194,55 @@ __device__ __forceinline__ void prefetch_run(const float4 *pts, uint32_t j, uint
     }
     if (L1) prefetch_l1(last); else prefetch_l2(last);
 }
+#ifndef PCC_THR_PIPE
+#define PCC_THR_PIPE 1
+#endif
+struct Quad { float4 p0, p1, p2, p3; };
+__device__ __forceinline__ Quad load_quad(const float4 *__restrict__ pts, uint32_t j) { Quad q; q.p0 = __ldg(pts + j); q.p1 = __ldg(pts + j + 1); q.p2 = __ldg(pts + j + 2); q.p3 = __ldg(pts + j + 3); return q; }
+template <uint32_t STRIDE, bool COMPRESS, class F>
+__device__ __forceinline__ void thr_quad(const Quad &q, const uint32_t j, const float x, const float y, const float z, float &T, float &dmin, float &tau, uint32_t &wa, const uint32_t cap, F &&on_full) {
+    const float d0 = dist2(x, y, z, q.p0.x, q.p0.y, q.p0.z), d1 = dist2(x, y, z, q.p1.x, q.p1.y, q.p1.z), d2 = dist2(x, y, z, q.p2.x, q.p2.y, q.p2.z), d3 = dist2(x, y, z, q.p3.x, q.p3.y, q.p3.z);
+    sts_v2(wa, __float_as_uint(d0), j); advance_if_le<STRIDE>(wa, d0, tau);
+    sts_v2(wa, __float_as_uint(d1), j + 1); advance_if_le<STRIDE>(wa, d1, tau);
+    sts_v2(wa, __float_as_uint(d2), j + 2); advance_if_le<STRIDE>(wa, d2, tau);
+    sts_v2(wa, __float_as_uint(d3), j + 3); advance_if_le<STRIDE>(wa, d3, tau);
+    dmin = fminf(fminf(dmin, fminf(d0, d1)), fminf(d2, d3)); tau = dmin + T;
+    if (!COMPRESS) wa = min(wa, cap);
+    else if (wa >= cap) on_full();                        // not clamped first: the entries in the sacrificial slots are real
+}
+// Software-pipelined: the four loads of step i+1 are issued before step i is processed (two register sets, loop unrolled by two), so
+// a warp keeps eight 16-byte loads in flight.  Measured motivation: with 4 warps per scheduler and one step in flight per warp, the
+// L2 round trip of a step (43 % of the sectors miss the small L1 left beside 192 KB of logs) was exposed on nearly every step.
 template <uint32_t STRIDE, bool COMPRESS, class F>
 __device__ __forceinline__ void thr_walk_run(const Grid &g, uint32_t j, const uint32_t e, const float x, const float y, const float z, float &T,
                                              float &dmin, float &tau, uint32_t &wa, const uint32_t cap, F &&on_full) {
-    for (; j + 4 <= e; j += 4) {
-        const float4 p0 = __ldg(g.pts + j), p1 = __ldg(g.pts + j + 1), p2 = __ldg(g.pts + j + 2), p3 = __ldg(g.pts + j + 3);
-        const float d0 = dist2(x, y, z, p0.x, p0.y, p0.z), d1 = dist2(x, y, z, p1.x, p1.y, p1.z), d2 = dist2(x, y, z, p2.x, p2.y, p2.z), d3 = dist2(x, y, z, p3.x, p3.y, p3.z);
-        sts_v2(wa, __float_as_uint(d0), j); advance_if_le<STRIDE>(wa, d0, tau);
-        sts_v2(wa, __float_as_uint(d1), j + 1); advance_if_le<STRIDE>(wa, d1, tau);
-        sts_v2(wa, __float_as_uint(d2), j + 2); advance_if_le<STRIDE>(wa, d2, tau);
-        sts_v2(wa, __float_as_uint(d3), j + 3); advance_if_le<STRIDE>(wa, d3, tau);
-        dmin = fminf(fminf(dmin, fminf(d0, d1)), fminf(d2, d3)); tau = dmin + T;
-        if (!COMPRESS) wa = min(wa, cap);
-        else if (wa >= cap) on_full();                    // not clamped first: the entries in the sacrificial slots are real
+#if PCC_THR_PIPE
+    bool have_a = j + 4 <= e;
+    Quad a, b;
+    if (have_a) a = load_quad(g.pts, j);
+    while (have_a) {
+        const bool have_b = j + 8 <= e;
+        if (have_b) b = load_quad(g.pts, j + 4);
+        thr_quad<STRIDE, COMPRESS>(a, j, x, y, z, T, dmin, tau, wa, cap, on_full);
+        j += 4;
+        if (!have_b) break;
+        have_a = j + 8 <= e;
+        if (have_a) a = load_quad(g.pts, j + 4);
+        thr_quad<STRIDE, COMPRESS>(b, j, x, y, z, T, dmin, tau, wa, cap, on_full);
+        j += 4;
     }
+#else
+#ifndef PCC_THR_EXP
+#define PCC_THR_EXP 0
+#endif
+    // PCC_THR_EXP (measurement builds only, results are wrong): 1 = every step re-reads the run's first four points (same sectors per
+    // lane: L1 hits, same wavefront count); 2 = every lane reads point 0 (one wavefront per load: pure issue cost)
+    const uint32_t j0 = j;
+    for (; j + 4 <= e; j += 4) {
+        const Quad a = load_quad(g.pts, PCC_THR_EXP == 1 ? j0 : (PCC_THR_EXP == 2 ? 0u : j));
+        thr_quad<STRIDE, COMPRESS>(a, j, x, y, z, T, dmin, tau, wa, cap, on_full);
+    }
+#endif
     if (j < e) {                                          // 1..3 left: the loads are clamped to the run, the extra lanes never advance
         const float4 p0 = __ldg(g.pts + j), p1 = __ldg(g.pts + min(j + 1, e - 1)), p2 = __ldg(g.pts + min(j + 2, e - 1));
         const float d0 = dist2(x, y, z, p0.x, p0.y, p0.z), d1 = dist2(x, y, z, p1.x, p1.y, p1.z), d2 = dist2(x, y, z, p2.x, p2.y, p2.z);
@@ -385,8 +420,9 @@ __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, 
         static_for<4>([&](auto I) { constexpr int i = decltype(I)::value; le[i] = (FULLK || q + i < k) ? slog[(best[q + i] & SMASK) * TH] : make_uint2(0u, 0u); });     // keys past k may be empty
         static_for<4>([&](auto I) { constexpr int i = decltype(I)::value; id[i] = __float_as_int(__ldg(&g.pts[le[i].y].w)); });
         if (FULLK && vec4) {
-            reinterpret_cast<int4 *>(oi)[q >> 2] = make_int4(id[0], id[1], id[2], id[3]);
-            reinterpret_cast<float4 *>(od)[q >> 2] = make_float4(__uint_as_float(le[0].x), __uint_as_float(le[1].x), __uint_as_float(le[2].x), __uint_as_float(le[3].x));
+            // streaming stores: the 1.28 GB result table is written once and must not evict the index from L2
+            __stcs(reinterpret_cast<int4 *>(oi) + (q >> 2), make_int4(id[0], id[1], id[2], id[3]));
+            __stcs(reinterpret_cast<float4 *>(od) + (q >> 2), make_float4(__uint_as_float(le[0].x), __uint_as_float(le[1].x), __uint_as_float(le[2].x), __uint_as_float(le[3].x)));
         } else {
             static_for<4>([&](auto I) { constexpr int i = decltype(I)::value; if (q + i < k) { oi[q + i] = id[i]; od[q + i] = __uint_as_float(le[i].x); } });
         }
