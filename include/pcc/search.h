@@ -162,6 +162,25 @@ int pcc_descriptor_nn(pcc_index *workspace, const float *ref, int64_t n_ref, con
 int pcc_export(const pcc_index *idx, double meta[16], void *ptrs[2]);
 int pcc_adopt(pcc_index *idx, const double meta[16], void *stream);   /* allocates; then fill via pcc_export ptrs */
 
+/* One process per GPU: `nccl_comm` is the caller's ncclComm_t over the ranks (not owned, must outlive the
+ * index; NULL detaches).  libnccl.so.2 is resolved with dlopen at this call -- the copy the process already loaded is the one
+ * used, so the communicator must come from it; libpcc_search has no link-time NCCL dependency.  After this call:
+ *   pcc_broadcast_index  the grid built on `root` (pcc_build) is adopted by every other rank: 16 doubles of description, then the
+ *                        sorted float4 points and the cell table straight into place (ncclBroadcast over NVLink)
+ *   pcc_gather           all-gather of per-shard result rows (DEVICE pointers).  Every rank passes its n_local rows of row_bytes
+ *                        bytes (a multiple of 4); `out` receives all n_total rows on every rank -- in ORIGINAL row order when
+ *                        `local_rows` (the original row number of each local row) is given, else concatenated in rank order
+ *   pcc_icp_align        `src` is this rank's shard of the source cloud; the 16 sums + count of every pass are all-reduced
+ *                        (17 doubles, ncclAllReduce), so every rank returns the same transform, iteration count and fitness
+ *   pcc_allreduce_f64    the same sum over n device doubles, for a consumer that drives pcc_icp_step itself
+ * Queries shard by construction (they are independent given the replicated grid): each rank simply calls pcc_knn / pcc_radius_* /
+ * pcc_normals_* / pcc_knn_mean_dist on its own rows; Euclidean clustering shards through pcc_ece_* below. */
+int pcc_comm_init(pcc_index *idx, void *nccl_comm, int rank, int world);
+int pcc_comm_info(const pcc_index *idx, int *rank, int *world);
+int pcc_broadcast_index(pcc_index *idx, int root, void *stream);
+int pcc_gather(pcc_index *idx, const void *local, int64_t n_local, int row_bytes, const int32_t *local_rows, void *out, int64_t n_total, void *stream);
+int pcc_allreduce_f64(pcc_index *idx, double *device_buf, int n, void *stream);
+
 /* time of the last query's dominant kernel in ms (CUDA events on the launch stream), < 0 if not recorded.
  * Recording is enabled with pcc_set_timing(idx, 1) and adds two events per call. */
 int pcc_set_timing(pcc_index *idx, int enable);

@@ -248,7 +248,8 @@ int pcc_icp_align(pcc_index *idx, const void *src, int64_t ns, int stride_bytes,
     }
     double prev_mse = DBL_MAX;
     const float *apply = nullptr;
-    struct OrderReset { pcc_index *i; ~OrderReset() { i->reuse_order_n = -1; } } order_reset{idx};   // also on the error returns below
+    struct OrderReset { pcc_index *i; ~OrderReset() { i->reuse_order_n = -1; i->icp_allreduce = false; } } order_reset{idx};   // also on the error returns below
+    idx->icp_allreduce = idx->comm != nullptr && idx->comm_world > 1;      // with a communicator `src` is this rank's shard of the source cloud
     idx->reuse_order_n = -1;
     idx->icp_prior_n = -1;        // a new alignment starts from the untransformed source: matches left by an earlier one are loose bounds (measured: first pass 31 ms with them, 17 ms without)
     static const bool trace = getenv("PCC_ICP_TRACE") != nullptr;     // per-pass kernel time on stderr (needs pcc_set_timing)

@@ -67,6 +67,9 @@ struct pcc_index {
     // scratch (grow-only, reused by every call on this index; calls on one index are serialised by the caller per stream)
     pcc::Buf raw, stage4, cellrank, qbuf, qkeys, qkeys2, qperm, qperm2, cub_tmp, out_i, out_f, out_l, keys64, keys64b, misc, parent, inv_pos, sel_params, icp_prior, calib;
     uint64_t grid_gen = 0;     // bumped by pcc_build / pcc_adopt
+    void *comm = nullptr;      // ncclComm_t handed to pcc_comm_init (not owned); rank / world of this process in it
+    int comm_rank = 0, comm_world = 1;
+    bool icp_allreduce = false;   // pcc_icp_step sums its 17 doubles over the ranks (set by pcc_icp_align while it runs on a sharded source)
     int calib_k = -1;          // k the logging-threshold table in `calib` was calibrated for (-1: none), on grid generation calib_gen of the grid owner
     uint64_t calib_gen = 0;
     int64_t calib_nq = 0;      // batch size of the call that last ran the block kernel (fallback monitor, see launch_knn_fast)
@@ -111,6 +114,7 @@ int prepare_queries(pcc_index *idx, const void *q, int64_t nq, int stride_bytes,
 int copy_out(void *dst, const void *src_dev, size_t bytes, int mem, cudaStream_t s);
 int rebuild_inverse(pcc_index *idx, cudaStream_t s);
 int rebuild_occupancy(pcc_index *idx, cudaStream_t s);   // occ bitmap from cell_start (after pcc_build / pcc_adopt)
+int comm_allreduce_f64(pcc_index *idx, double *d_buf, int n, cudaStream_t s);   // pcc_comm.cu; no-op without a communicator
 // k > 32: neighbours by selection (pcc_radius.cu); rows are sorted by (d2, index), oi / od are device pointers
 int knn_select(pcc_index *idx, const Queries &qs, int k, int32_t *oi, float *od, cudaStream_t s);
 struct KernelTimer {

@@ -1201,6 +1201,7 @@ int pcc_icp_step(pcc_index *idx, void *src_inout, int64_t ns, int stride_bytes, 
     PCC_LAUNCHED();
     icp_reduce_kernel<<<17, 256, 0, s>>>(partials, nb, d_out);
     PCC_LAUNCHED();
+    if (idx->icp_allreduce) PCC_TRY(comm_allreduce_f64(idx, d_out, 17, s));      // sharded source cloud: the sums of every rank's shard (NCCL)
     PCC_CUDA(cudaGetLastError());
     timer.stop();
     double *h = (double *)idx->h_pinned;

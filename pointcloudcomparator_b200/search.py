@@ -39,8 +39,9 @@ def _rows(a):
     return a.ctypes.data, a.shape[0], (a.strides[0] if a.shape[0] > 1 else a.shape[1] * 4), HOST, a
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream) if torch is not None and torch.cuda.is_available() else None
+def _stream(device=None):
+    """torch's current stream ON THE INDEX'S DEVICE (the library launches there whatever torch's current device is)."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream) if torch is not None and torch.cuda.is_available() else None
 
 
 class GridSearch:
@@ -82,7 +83,7 @@ class GridSearch:
             else:
                 ikeep = np.ascontiguousarray(indices, np.int32)
                 ip, ni = ikeep.ctypes.data, ikeep.size
-        check(self._L.pcc_build(self._h, ptr, n, stride, ip, ni, float(cell_hint), int(k_hint), mem, _stream()))
+        check(self._L.pcc_build(self._h, ptr, n, stride, ip, ni, float(cell_hint), int(k_hint), mem, _stream(self.device)))
         self._cloud, self._mem, self._n_input = keep, mem, n
         return self
 
@@ -118,7 +119,7 @@ class GridSearch:
         idx, ip = self._alloc(mem, (rows, k), np.int32)
         d2, dp = self._alloc(mem, (rows, k), np.float32)
         keff = C.c_int()
-        check(self._L.pcc_knn(self._h, ptr, nq, stride, int(k), ip, dp, C.byref(keff), mem, _stream()))
+        check(self._L.pcc_knn(self._h, ptr, nq, stride, int(k), ip, dp, C.byref(keff), mem, _stream(self.device)))
         return idx, d2, keff.value
 
     def radiusSearch(self, queries, radius: float, max_nn: int = 0):
@@ -126,10 +127,10 @@ class GridSearch:
         ptr, nq, stride, mem, keep, rows = self._queries(queries)
         off, op = self._alloc(mem, (rows + 1,), np.int64)
         total = C.c_int64()
-        check(self._L.pcc_radius_count(self._h, ptr, nq, stride, float(radius), int(max_nn), op, C.byref(total), mem, _stream()))
+        check(self._L.pcc_radius_count(self._h, ptr, nq, stride, float(radius), int(max_nn), op, C.byref(total), mem, _stream(self.device)))
         idx, ip = self._alloc(mem, (max(total.value, 1),), np.int32)
         d2, dp = self._alloc(mem, (max(total.value, 1),), np.float32)
-        check(self._L.pcc_radius_fill(self._h, ptr, nq, stride, float(radius), int(max_nn), int(self._sorted), op, ip, dp, mem, _stream()))
+        check(self._L.pcc_radius_fill(self._h, ptr, nq, stride, float(radius), int(max_nn), int(self._sorted), op, ip, dp, mem, _stream(self.device)))
         return off, idx[: total.value], d2[: total.value]
 
     # ---- fused consumers -----------------------------------------------------------------------
@@ -137,7 +138,7 @@ class GridSearch:
         """StatisticalOutlierRemoval first pass: mean distance to the mean_k nearest (self dropped)."""
         ptr, nq, stride, mem, keep, rows = self._queries(queries)
         out, op = self._alloc(mem, (rows,), np.float32)
-        check(self._L.pcc_knn_mean_dist(self._h, ptr, nq, stride, int(mean_k), op, mem, _stream()))
+        check(self._L.pcc_knn_mean_dist(self._h, ptr, nq, stride, int(mean_k), op, mem, _stream(self.device)))
         return out
 
     def sorThreshold(self, distances, n_valid: int, std_mul: float):
@@ -149,21 +150,21 @@ class GridSearch:
         stats = (C.c_double * 3)()
         kept = C.c_int64()
         dp = distances.data_ptr() if mem == DEVICE else distances.ctypes.data
-        check(self._L.pcc_sor_threshold(self._h, dp, n, int(n_valid), float(std_mul), stats, kp, C.byref(kept), mem, _stream()))
+        check(self._L.pcc_sor_threshold(self._h, dp, n, int(n_valid), float(std_mul), stats, kp, C.byref(kept), mem, _stream(self.device)))
         return dict(mean=stats[0], stddev=stats[1], threshold=stats[2], kept=kept.value, keep=keep)
 
     def normalsKnn(self, queries, k: int, viewpoint=(0.0, 0.0, 0.0)):
         ptr, nq, stride, mem, keep, rows = self._queries(queries)
         out, op = self._alloc(mem, (rows, 4), np.float32)
         vp = (C.c_float * 3)(*[float(v) for v in viewpoint])
-        check(self._L.pcc_normals_knn(self._h, ptr, nq, stride, int(k), vp, op, mem, _stream()))
+        check(self._L.pcc_normals_knn(self._h, ptr, nq, stride, int(k), vp, op, mem, _stream(self.device)))
         return out
 
     def normalsRadius(self, queries, radius: float, viewpoint=(0.0, 0.0, 0.0)):
         ptr, nq, stride, mem, keep, rows = self._queries(queries)
         out, op = self._alloc(mem, (rows, 4), np.float32)
         vp = (C.c_float * 3)(*[float(v) for v in viewpoint])
-        check(self._L.pcc_normals_radius(self._h, ptr, nq, stride, float(radius), vp, op, mem, _stream()))
+        check(self._L.pcc_normals_radius(self._h, ptr, nq, stride, float(radius), vp, op, mem, _stream(self.device)))
         return out
 
     def icpStep(self, source, T_apply=None, want_correspondences: bool = False):
@@ -179,7 +180,7 @@ class GridSearch:
         if want_correspondences:
             ci, ip = self._alloc(mem, (ns,), np.int32)
             cd, dp = self._alloc(mem, (ns,), np.float32)
-        check(self._L.pcc_icp_step(self._h, ptr, ns, stride, Tp, sums, C.byref(cnt), ip, dp, mem, _stream()))
+        check(self._L.pcc_icp_step(self._h, ptr, ns, stride, Tp, sums, C.byref(cnt), ip, dp, mem, _stream(self.device)))
         return cnt.value, np.array(sums[:], np.float64), ci, cd
 
     def icpAlign(self, source, max_iter: int = 20):
@@ -187,7 +188,7 @@ class GridSearch:
         ptr, ns, stride, mem, keep = _rows(source)
         T = (C.c_float * 16)()
         conv, it, fit = C.c_int(), C.c_int(), C.c_double()
-        check(self._L.pcc_icp_align(self._h, ptr, ns, stride, int(max_iter), T, C.byref(conv), C.byref(fit), C.byref(it), mem, _stream()))
+        check(self._L.pcc_icp_align(self._h, ptr, ns, stride, int(max_iter), T, C.byref(conv), C.byref(fit), C.byref(it), mem, _stream(self.device)))
         return dict(T=np.array(T[:], np.float32).reshape(4, 4), converged=bool(conv.value), fitness=fit.value, iterations=it.value)
 
     def euclideanClusters(self, tolerance: float, min_size: int = 1, max_size: int = 2**31 - 1):
@@ -197,36 +198,65 @@ class GridSearch:
         cap = max(self._n_input // max(int(min_size), 1) + 1, 1)
         sizes, sp = self._alloc(mem, (cap,), np.int64)
         nc = C.c_int64()
-        check(self._L.pcc_euclidean_labels(self._h, float(tolerance), int(min_size), int(max_size), lp, C.byref(nc), sp, cap, mem, _stream()))
+        check(self._L.pcc_euclidean_labels(self._h, float(tolerance), int(min_size), int(max_size), lp, C.byref(nc), sp, cap, mem, _stream(self.device)))
         return labels[: self._n_input], sizes[: nc.value]
 
     # ---- sharded clustering primitives (device tensors; forests over SORTED positions, see include/pcc/search.h) ----
     def eceNewForest(self):
         parent = torch.empty(max(self.size, 1), dtype=torch.int32, device=f"cuda:{self.device}")
-        check(self._L.pcc_ece_init(self._h, parent.data_ptr(), _stream()))
+        check(self._L.pcc_ece_init(self._h, parent.data_ptr(), _stream(self.device)))
         return parent
 
     def eceLinkRange(self, parent, tolerance: float, begin: int, end: int):
-        check(self._L.pcc_ece_link_range(self._h, float(tolerance), int(begin), int(end), parent.data_ptr(), _stream()))
+        check(self._L.pcc_ece_link_range(self._h, float(tolerance), int(begin), int(end), parent.data_ptr(), _stream(self.device)))
 
     def eceAbsorb(self, parent, other):
-        check(self._L.pcc_ece_absorb(self._h, other.data_ptr(), parent.data_ptr(), _stream()))
+        check(self._L.pcc_ece_absorb(self._h, other.data_ptr(), parent.data_ptr(), _stream(self.device)))
 
     def eceFinish(self, parent, min_size: int = 1, max_size: int = 2**31 - 1):
         labels = torch.empty(max(self._n_input, 1), dtype=torch.int32, device=f"cuda:{self.device}")
         cap = max(self._n_input // max(int(min_size), 1) + 1, 1)
         sizes = torch.empty(cap, dtype=torch.int64, device=f"cuda:{self.device}")
         nc = C.c_int64()
-        check(self._L.pcc_ece_finish(self._h, parent.data_ptr(), int(min_size), int(max_size), labels.data_ptr(), C.byref(nc), sizes.data_ptr(), cap, _stream()))
+        check(self._L.pcc_ece_finish(self._h, parent.data_ptr(), int(min_size), int(max_size), labels.data_ptr(), C.byref(nc), sizes.data_ptr(), cap, _stream(self.device)))
         return labels[: self._n_input], sizes[: nc.value]
 
     def firstWithin(self, queries, thr: float):
         ptr, nq, stride, mem, keep = _rows(queries)
         out, op = self._alloc(mem, (nq,), np.int32)
-        check(self._L.pcc_first_within(self._h, ptr, nq, stride, float(thr), op, mem, _stream()))
+        check(self._L.pcc_first_within(self._h, ptr, nq, stride, float(thr), op, mem, _stream(self.device)))
         return out
 
     # ---- measurement + multi-GPU plumbing ----------------------------------------------------------
+    # ---- multi-GPU (include/pcc/search.h: pcc_comm_init / pcc_broadcast_index / pcc_gather) ----------------------
+    def commInit(self, nccl_comm, rank: int, world: int):
+        """Attach the caller's ncclComm_t (an integer handle, e.g. from shard.nccl_comm) to this index."""
+        check(self._L.pcc_comm_init(self._h, C.c_void_p(int(nccl_comm) if nccl_comm else 0), int(rank), int(world)))
+        return self
+
+    def broadcastIndex(self, root: int = 0):
+        """Every rank but `root` adopts the grid `root` built (NCCL broadcast straight into the device arrays)."""
+        check(self._L.pcc_broadcast_index(self._h, int(root), _stream(self.device)))
+        self._mem = DEVICE
+        self._n_input = int(self._meta()[1])
+        return self
+
+    def _meta(self):
+        meta = (C.c_double * 16)()
+        ptrs = (C.c_void_p * 2)()
+        check(self._L.pcc_export(self._h, meta, ptrs))
+        return np.array(meta[:], np.float64)
+
+    def gather(self, local, rows, n_total: int):
+        """All-gather of per-shard result rows (CUDA tensors): `local` [n_local, ...] 4-byte elements, `rows` the original row number
+        of each local row (int32/int64 tensor) or None (rank-order concatenation).  Returns the full [n_total, ...] table."""
+        assert _is_cuda(local) and local.is_contiguous() and local.element_size() == 4
+        row_bytes = int(np.prod(local.shape[1:], dtype=np.int64)) * 4 if local.dim() > 1 else 4
+        out = torch.empty((int(n_total),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        r32 = None if rows is None else rows.to(torch.int32).contiguous()
+        check(self._L.pcc_gather(self._h, local.data_ptr(), local.shape[0], row_bytes, None if r32 is None else r32.data_ptr(), out.data_ptr(), int(n_total), _stream(self.device)))
+        return out
+
     def setTiming(self, enable: bool):
         check(self._L.pcc_set_timing(self._h, int(enable)))
 
@@ -242,7 +272,7 @@ class GridSearch:
 
     def adopt(self, meta):
         m = (C.c_double * 16)(*[float(v) for v in meta])
-        check(self._L.pcc_adopt(self._h, m, _stream()))
+        check(self._L.pcc_adopt(self._h, m, _stream(self.device)))
         self._n_input, self._mem = int(meta[1]), DEVICE
         return self.export()
 
@@ -260,7 +290,7 @@ def voxel_grid(rows, leaf, rgb_offset_bytes: int = -1, min_points: int = 0, devi
         out = np.zeros((n, stride // 4), np.float32)
         op = out.ctypes.data
     n_out = C.c_int64()
-    check(ws._L.pcc_voxel_grid(ws._h, ptr, n, stride, int(rgb_offset_bytes), lf, int(min_points), op, C.byref(n_out), mem, _stream()))
+    check(ws._L.pcc_voxel_grid(ws._h, ptr, n, stride, int(rgb_offset_bytes), lf, int(min_points), op, C.byref(n_out), mem, _stream(ws.device)))
     return out[: n_out.value]
 
 
@@ -280,11 +310,11 @@ def descriptor_nn(ref, qry, device: int = 0, workspace: "GridSearch | None" = No
     if _is_cuda(ref):
         assert ref.dtype == torch.float32 and qry.dtype == torch.float32 and ref.stride(1) == 1 and qry.stride(1) == 1 and ref.stride(0) == qry.stride(0)
         idx = torch.empty(qry.shape[0], dtype=torch.int32, device=ref.device); d2 = torch.empty(qry.shape[0], dtype=torch.float32, device=ref.device)
-        check(ws._L.pcc_descriptor_nn(ws._h, ref.data_ptr(), ref.shape[0], qry.data_ptr(), qry.shape[0], ref.shape[1], ref.stride(0), idx.data_ptr(), d2.data_ptr(), DEVICE, _stream()))
+        check(ws._L.pcc_descriptor_nn(ws._h, ref.data_ptr(), ref.shape[0], qry.data_ptr(), qry.shape[0], ref.shape[1], ref.stride(0), idx.data_ptr(), d2.data_ptr(), DEVICE, _stream(ws.device)))
         return idx, d2
     ref, qry = np.ascontiguousarray(ref, np.float32), np.ascontiguousarray(qry, np.float32)
     idx, d2 = np.empty(qry.shape[0], np.int32), np.empty(qry.shape[0], np.float32)
-    check(ws._L.pcc_descriptor_nn(ws._h, ref.ctypes.data, ref.shape[0], qry.ctypes.data, qry.shape[0], ref.shape[1], ref.shape[1], idx.ctypes.data, d2.ctypes.data, HOST, _stream()))
+    check(ws._L.pcc_descriptor_nn(ws._h, ref.ctypes.data, ref.shape[0], qry.ctypes.data, qry.shape[0], ref.shape[1], ref.shape[1], idx.ctypes.data, d2.ctypes.data, HOST, _stream(ws.device)))
     return idx, d2
 
 

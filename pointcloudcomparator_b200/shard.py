@@ -133,6 +133,54 @@ def euclidean_clusters_sharded(search, tolerance: float, min_size: int, max_size
     return search.eceFinish(parent, min_size, max_size)
 
 
+# ---- C-ABI multi-GPU path: an NCCL communicator of our own, handed to libpcc_search (pcc_comm_init) ----------------------------
+_NCCL = None
+
+
+def _nccl():
+    """libnccl.so.2 as the process already has it (torch's bundled copy once torch is imported); libpcc_search dlopens the same one."""
+    import ctypes
+    global _NCCL
+    if _NCCL is None:
+        _NCCL = ctypes.CDLL("libnccl.so.2", mode=ctypes.RTLD_GLOBAL)
+        _NCCL.ncclGetErrorString.restype = ctypes.c_char_p
+    return _NCCL
+
+
+def nccl_comm(device: int, group=None) -> int:
+    """ncclCommInitRank over the ranks of `group` (the 128-byte unique id travels through torch.distributed).  Returns the
+    ncclComm_t as an integer; pass it to GridSearch.commInit.  The communicator lives until the process exits."""
+    import ctypes
+
+    class _Uid(ctypes.Structure):
+        _fields_ = [("internal", ctypes.c_char * 128)]
+
+    lib = _nccl()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    uid = _Uid()
+    if rank == 0:
+        rc = lib.ncclGetUniqueId(ctypes.byref(uid))
+        if rc != 0:
+            raise RuntimeError(f"ncclGetUniqueId: {lib.ncclGetErrorString(rc).decode()}")
+    box = [bytes(uid) if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    uid = _Uid.from_buffer_copy(box[0])
+    torch.cuda.set_device(device)
+    comm = ctypes.c_void_p()
+    lib.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _Uid, ctypes.c_int]
+    rc = lib.ncclCommInitRank(ctypes.byref(comm), world, uid, rank)
+    if rc != 0:
+        raise RuntimeError(f"ncclCommInitRank: {lib.ncclGetErrorString(rc).decode()}")
+    return int(comm.value)
+
+
+def attach(search, group=None):
+    """Create a communicator over `group` and attach it to `search` (pcc_comm_init).  Returns (rank, world)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    search.commInit(nccl_comm(search.device, group), rank, world)
+    return rank, world
+
+
 def broadcast_grid(search, src: int = 0, group=None):
     """Rank `src` has a built GridSearch; every other rank adopts its grid (meta via broadcast_object_list,
     the float4 points and the cell-start table via NCCL broadcast straight into the adopted device arrays)."""

@@ -47,7 +47,38 @@ cnt, sums, _, _ = t.icpStep(torch.from_numpy(np.ascontiguousarray(mine)).cuda(),
 sums, cnt = shard.allreduce_sums(sums, cnt, device=dev)
 ocnt, osums, _, _ = oracle.KdTree(tgt).icp_pass(src[:, :3])
 assert cnt == ocnt and np.allclose(sums, osums, rtol=1e-11, atol=1e-8), "sharded ICP sums mismatch"
+
+# 5. the same through the C ABI's own multi-GPU entry points (pcc_comm_init / pcc_broadcast_index / pcc_gather / sharded pcc_icp_align)
+c = GridSearch(local)
+shard.attach(c)
+if rank == 0:
+    c.setInputCloud(torch.from_numpy(pts).cuda(), cell_hint=0.05)
+c.broadcastIndex(0)
+assert c.size == len(pts) and c.grid_info() == s.grid_info()
+mine, rows = shard.shard_queries(qry, rank, world, origin, g["cell"], g["dims"])
+ci, cd, _ = c.nearestKSearch(torch.from_numpy(mine).cuda(), 16)
+drows = torch.from_numpy(rows).to(dev)
+assert np.array_equal(c.gather(ci, drows, len(qry)).cpu().numpy(), oi), "pcc_gather (indices) mismatch"
+assert np.array_equal(c.gather(cd, drows, len(qry)).cpu().numpy().view(np.uint32), od.view(np.uint32)), "pcc_gather (d2) mismatch"
+cat = c.gather(ci, None, len(qry)).cpu().numpy()                 # rank-order concatenation
+b0, e0 = shard.shard_ranges(len(qry), world)[rank]
+assert np.array_equal(cat[b0:e0], ci.cpu().numpy())
+# sharded ICP: every rank aligns its slice of the source; result must equal the single-GPU alignment up to fp64 summation order
+t2 = GridSearch(local)
+shard.attach(t2)
+if rank == 0:
+    t2.setInputCloud(torch.from_numpy(tgt).cuda(), k_hint=8)
+t2.broadcastIndex(0)
+b1, e1 = shard.shard_ranges(len(src), world)[rank]
+r_sh = t2.icpAlign(torch.from_numpy(np.ascontiguousarray(src[b1:e1])).cuda(), 20)
+ref_icp = oracle.icp(src, tgt, 20)
+assert r_sh["converged"] == ref_icp["converged"] and abs(r_sh["iterations"] - ref_icp["iterations"]) <= 1
+assert np.allclose(r_sh["T"], ref_icp["T"], atol=2e-5) and np.isclose(r_sh["fitness"], ref_icp["fitness"], rtol=1e-3)
+Tall = [None] * world
+dist.all_gather_object(Tall, r_sh["T"].tobytes())
+assert all(x == Tall[0] for x in Tall), "ranks disagree on the ICP transform"
 dist.barrier()
 if rank == 0:
-    print(f"MULTI_GPU_CHECK PASS world={world}: broadcast grid, sharded kNN gather, sharded clustering ({len(sizes)} clusters), ICP sums", flush=True)
+    print(f"MULTI_GPU_CHECK PASS world={world}: broadcast grid, sharded kNN gather, sharded clustering ({len(sizes)} clusters), ICP sums; "
+          f"C ABI: pcc_comm_init + pcc_broadcast_index + pcc_gather + sharded pcc_icp_align ({r_sh['iterations']} iterations)", flush=True)
 dist.destroy_process_group()

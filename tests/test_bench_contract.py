@@ -8,8 +8,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(*args):
-    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, timeout=300)
+def _run(*args, env=None):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, timeout=300, env=env)
 
 
 def test_reference_arm_prints_one_json_line():
@@ -33,3 +33,13 @@ def test_product_arm_needs_cuda():
     out = _run("--ref-points", "1000", "--queries", "1000", "--steps", "1")
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
     assert out.stdout.strip() == ""
+
+
+def test_reference_arm_ignores_omp_num_threads_1():
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the reference arm must still use every core it may run on, so that the
+    CPU baseline is the same at every --gpus N (round-1 VERDICT: the N >= 2 ratios were void because `cores` fell to 1)."""
+    avail = len(os.sched_getaffinity(0))
+    out = _run("--impl", "reference", "--gpus", "2", "--ref-points", "60000", "--queries", "20000", "--steps", "1", "--warmup", "1", env={**os.environ, "OMP_NUM_THREADS": "1"})
+    assert out.returncode == 0, out.stderr
+    d = json.loads([ln for ln in out.stdout.splitlines() if ln.strip()][0])
+    assert d["cpu_baseline"]["cores"] == avail and d["n_gpus"] == 2 and d["scaling"] == "strong"
