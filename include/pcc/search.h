@@ -149,9 +149,11 @@ int pcc_region_growing(const int32_t *neighbours, int64_t n, int k, const float 
                        int64_t min_size, int64_t max_size, int32_t *labels, int64_t *n_clusters);
 
 /* matchRIFTFeaturesKnn (src/comparator.cpp:560-588): KdTreeFLANN<Histogram<32>> over `ref`, nearestKSearch(k = 1) for every row
- * of `qry` [up].  Exact brute force in descriptor space: d2 accumulated sequentially over the `dim` floats of a row (fp32, no
- * FMA), ties to the lowest index, non-finite reference rows skipped, non-finite queries get (-1, +inf).  The caller applies
- * the reference's acceptance test (d2 < 0.05f).  dim = 32 (RIFT32) is instantiated; rows are stride_floats floats apart. */
+ * of `qry` [up].  Exact brute force in descriptor space: d2 accumulated sequentially over the first `dim` floats of a row (fp32, no
+ * FMA), ties to the lowest index, reference rows that are non-finite in those floats skipped, such queries get (-1, +inf).  The
+ * caller applies the reference's acceptance test (d2 < 0.05f).  Rows are stride_floats floats apart (32 for RIFT32).
+ * dim = 3 is REFERENCE-EXACT: the reference neither registers Histogram<32> nor sets a point representation, so PCL 1.7's
+ * DefaultPointRepresentation clamps the tree to the first 3 floats [up]; dim = 32 compares all bins (what the author intended). */
 int pcc_descriptor_nn(pcc_index *workspace, const float *ref, int64_t n_ref, const float *qry, int64_t n_qry, int dim, int stride_floats,
                       int32_t *out_idx, float *out_d2, int mem, void *stream);
 

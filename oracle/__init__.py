@@ -226,14 +226,16 @@ def voxel_grid(rows, leaf, rgb_offset_floats: int = -1, min_points: int = 0):
     leaf = np.ascontiguousarray(np.broadcast_to(np.asarray(leaf, np.float32), (3,)))
     out = np.zeros_like(rows)
     n = lib().orc_voxel_grid(_p(rows, C.c_float), rows.shape[0], rows.shape[1], rgb_offset_floats, _p(leaf, C.c_float), min_points, _p(out, C.c_float))
-    if n < 0:
-        raise ValueError("leaf size is too small for the input dataset")
     return out[:n]
 
 
-def descriptor_nn(ref, qry):
-    """matchRIFTFeaturesKnn's inner search: nearest reference descriptor of every query descriptor (index or -1, d2)."""
-    ref, qry = np.ascontiguousarray(ref, np.float32), np.ascontiguousarray(qry, np.float32)
+def descriptor_nn(ref, qry, dims: int | None = None):
+    """matchRIFTFeaturesKnn's inner search: nearest reference descriptor of every query descriptor (index or -1, d2), over the
+    first `dims` floats of a row (None = all; 3 = PCL 1.7's DefaultPointRepresentation clamp for an unregistered Histogram<32>)."""
+    ref, qry = np.asarray(ref, np.float32), np.asarray(qry, np.float32)
+    if dims is not None:
+        ref, qry = ref[:, :dims], qry[:, :dims]
+    ref, qry = np.ascontiguousarray(ref), np.ascontiguousarray(qry)
     idx, d2 = np.empty(qry.shape[0], np.int32), np.empty(qry.shape[0], np.float32)
     lib().orc_descriptor_nn(_p(ref, C.c_float), ref.shape[0], _p(qry, C.c_float), qry.shape[0], ref.shape[1], _p(idx, C.c_int32), _p(d2, C.c_float))
     return idx, d2

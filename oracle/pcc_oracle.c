@@ -703,7 +703,15 @@ ORC_API int64_t orc_voxel_grid(const float *pts, int64_t n, int stride_f, int rg
         min_b[d] = (int)floorf(mn[d] * inv[d]);
         div[d] = (int64_t)((int)floorf(mx[d] * inv[d])) - min_b[d] + 1;
     }
-    if ((double)div[0] * (double)div[1] * (double)div[2] > 2147483647.0) return -1;      /* "Leaf size is too small" */
+    {   /* PCL 1.7 VoxelGrid::applyFilter [upstream]: dx*dy*dz > INT_MAX -> PCL_WARN("Leaf size is too small ...") and `output = *input_`:
+         * the cloud passes through unfiltered, every row (also the non-finite ones) */
+        double dchk = 1.0;
+        for (int d = 0; d < 3; ++d) dchk *= (double)((int64_t)((mx[d] - mn[d]) * inv[d]) + 1);
+        if (dchk > 2147483647.0 || (double)div[0] * (double)div[1] * (double)div[2] > 2147483647.0) {
+            memcpy(out, pts, sizeof(float) * (size_t)n * (size_t)stride_f);
+            return n;
+        }
+    }
     mul[0] = 1; mul[1] = (int)div[0]; mul[2] = (int)(div[0] * div[1]);
     orc_vx *v = (orc_vx *)malloc(sizeof(orc_vx) * (size_t)m);
     int64_t c = 0;

@@ -26,7 +26,7 @@ int fail(int code, const char *fmt, ...) {
 }
 
 static constexpr int kMaxDim = 2048;                 // covered_d2()'s rounding margin assumes this cap
-static constexpr int64_t kMaxCellsDefault = 1ll << 28;
+static constexpr int64_t kMaxCellsDefault = 1ll << 28;      // hard cap: knn_rings_kernel packs (first cell | (cells - 1) << 28) in one uint32 (pcc_knn.cu)
 
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
 static inline float ord2f(int i) { int j = i >= 0 ? i : i ^ 0x7FFFFFFF; float f; memcpy(&f, &j, 4); return f; }
@@ -169,7 +169,7 @@ static double clamp_cell(const double ext[3], double cell, int64_t max_cells) {
 int prepare_queries(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int mem, cudaStream_t s, Queries *out) {
     if (!idx->built) return fail(PCC_ERR_STATE, "index not built (call pcc_build first)");
     if (q == nullptr) { out->self = true; out->nq = idx->n_indexed; out->rows = idx->n_input; out->q = nullptr; out->order = nullptr; return PCC_OK; }
-    if (nq < 0 || stride_bytes < 12 || (stride_bytes & 3)) return fail(PCC_ERR_INVALID, "bad query batch (nq=%lld stride=%d)", (long long)nq, stride_bytes);
+    if (nq < 0 || nq >= (1ll << 31) - 1 || stride_bytes < 12 || (stride_bytes & 3)) return fail(PCC_ERR_INVALID, "bad query batch (nq=%lld stride=%d; nq must be below 2^31 - 1: row counts go to CUB as 32-bit ints)", (long long)nq, stride_bytes);
     out->self = false; out->nq = nq; out->rows = nq;
     if (nq == 0) return PCC_OK;
     const uint8_t *raw = (const uint8_t *)q;
@@ -281,6 +281,7 @@ int pcc_build(pcc_index *idx, const void *pts, int64_t n, int stride_bytes, cons
     if (!idx) return fail(PCC_ERR_INVALID, "idx is NULL");
     if (n < 0 || (n > 0 && !pts) || stride_bytes < 12 || (stride_bytes & 3)) return fail(PCC_ERR_INVALID, "bad cloud (n=%lld stride=%d)", (long long)n, stride_bytes);
     if (n >= (1ll << 31) - 1) return fail(PCC_ERR_INVALID, "n=%lld exceeds int32 indices", (long long)n);
+    if (indices && (n_idx < 0 || n_idx >= (1ll << 31) - 1)) return fail(PCC_ERR_INVALID, "n_idx=%lld out of range", (long long)n_idx);
     cudaStream_t s = (cudaStream_t)stream;
     PCC_CUDA(cudaSetDevice(idx->device));
     idx->built = false;
@@ -325,6 +326,7 @@ int pcc_build(pcc_index *idx, const void *pts, int64_t n, int stride_bytes, cons
     PCC_CUDA(cudaStreamSynchronize(s));
     const int64_t nfin = (int64_t)(*(unsigned long long *)(h + 8));
     idx->n_indexed = nfin;
+    idx->all_rows_indexed = !indices && nfin == n;       // an `indices` list may repeat or skip rows even when the counts agree
     if (nfin == 0) {   // empty index: every query returns nothing
         PCC_TRY(idx->pts.reserve(sizeof(float4)));
         PCC_TRY(idx->cell_start.reserve(2 * sizeof(uint32_t)));
@@ -339,7 +341,7 @@ int pcc_build(pcc_index *idx, const void *pts, int64_t n, int stride_bytes, cons
 
     // 2. cell size: caller's hint, or iterate on the measured occupancy of non-empty cells
     int64_t max_cells = kMaxCellsDefault;
-    if (const char *e = getenv("PCC_MAX_CELLS")) { long long v = atoll(e); if (v >= 1) max_cells = v; }
+    if (const char *e = getenv("PCC_MAX_CELLS")) { long long v = atoll(e); if (v >= 1) max_cells = std::min<long long>(v, kMaxCellsDefault); }   // never above 2^28: knn_rings_kernel packs a cell index in 28 bits
     const double mx = std::max(ext[0], std::max(ext[1], ext[2]));
     double cell;
     const bool autotune = !(cell_hint > 0);
@@ -412,7 +414,7 @@ int pcc_export(const pcc_index *idx, double meta[16], void *ptrs[2]) {
     meta[2] = idx->gh.nx; meta[3] = idx->gh.ny; meta[4] = idx->gh.nz;
     meta[5] = idx->gh.ox; meta[6] = idx->gh.oy; meta[7] = idx->gh.oz;
     meta[8] = idx->gh.cell; meta[9] = idx->gh.inv_cell; meta[10] = idx->gh.occupancy; meta[11] = (double)idx->gh.n_cells;
-    meta[12] = meta[13] = meta[14] = meta[15] = 0;
+    meta[12] = idx->all_rows_indexed ? 1.0 : 0.0; meta[13] = meta[14] = meta[15] = 0;
     ptrs[0] = idx->pts.p; ptrs[1] = idx->cell_start.p;
     return PCC_OK;
 }
@@ -421,7 +423,10 @@ int pcc_adopt(pcc_index *idx, const double meta[16], void *stream) {
     if (!idx) return fail(PCC_ERR_INVALID, "idx is NULL");
     (void)stream;
     PCC_CUDA(cudaSetDevice(idx->device));
-    idx->n_indexed = (int64_t)meta[0]; idx->n_input = (int64_t)meta[1];
+    if (!(meta[0] >= 0 && meta[1] >= 0 && meta[0] < 2147483647.0 && meta[1] < 2147483647.0 && meta[2] >= 1 && meta[3] >= 1 && meta[4] >= 1 && meta[2] <= 2048 && meta[3] <= 2048 && meta[4] <= 2048 &&
+          meta[11] >= 1 && meta[11] <= (double)kMaxCellsDefault && meta[11] == meta[2] * meta[3] * meta[4] && meta[8] > 0))
+        return fail(PCC_ERR_INVALID, "pcc_adopt: grid description out of range (n=%g dims=%gx%gx%g cells=%g cell=%g)", meta[0], meta[2], meta[3], meta[4], meta[11], meta[8]);
+    idx->n_indexed = (int64_t)meta[0]; idx->n_input = (int64_t)meta[1]; idx->all_rows_indexed = meta[12] == 1.0;
     idx->gh.nx = (int)meta[2]; idx->gh.ny = (int)meta[3]; idx->gh.nz = (int)meta[4];
     idx->gh.ox = (float)meta[5]; idx->gh.oy = (float)meta[6]; idx->gh.oz = (float)meta[7];
     idx->gh.cell = (float)meta[8]; idx->gh.inv_cell = (float)meta[9]; idx->gh.occupancy = meta[10]; idx->gh.n_cells = (int64_t)meta[11];

@@ -6,6 +6,13 @@
 // brute force: one thread per query descriptor, reference descriptors staged through shared memory in tiles, squared
 // L2 accumulated sequentially over the dimensions in fp32 without FMA (FLANN L2_Simple), ties broken by index.
 // Non-finite reference descriptors are skipped (KdTreeFLANN::setInputCloud); a non-finite query has no match.
+//
+// `dim` = the number of LEADING floats of a descriptor row that take part (distance and the finiteness test); rows are
+// stride_floats apart.  The reference never registers pcl::Histogram<32> as a point struct and passes no point representation, so
+// PCL 1.7's DefaultPointRepresentation<PointT> applies: nr_dimensions_ = sizeof(PointT) / sizeof(float) CLAMPED TO 3
+// (pcl/point_representation.h [up]) -- the reference binary builds a 3-D tree over the first three histogram bins and its
+// `squaredDistances[0] < 0.05f` test sees only those.  dim = 3 is therefore the reference-exact setting and dim = 32 what the
+// author presumably intended; both are instantiated, the host mirrors default to 3.
 #include <algorithm>
 #include <cmath>
 
@@ -59,7 +66,7 @@ extern "C" int pcc_descriptor_nn(pcc_index *ws, const float *ref, int64_t n_ref,
                                  int32_t *out_idx, float *out_d2, int mem, void *stream) {
     if (!ws) return fail(PCC_ERR_INVALID, "workspace index is NULL");
     if (n_ref < 0 || n_qry < 0 || (n_ref > 0 && !ref) || (n_qry > 0 && (!qry || !out_idx || !out_d2)) || stride_floats < dim) return fail(PCC_ERR_INVALID, "bad arguments");
-    if (dim != 32) return fail(PCC_ERR_INVALID, "descriptor dimension %d is not instantiated (32 = RIFT32 is)", dim);
+    if (dim != 32 && dim != 3) return fail(PCC_ERR_INVALID, "descriptor dimension %d is not instantiated (3 = what PCL 1.7 compares for Histogram<32>, 32 = all RIFT32 bins)", dim);
     PCC_CUDA(cudaSetDevice(ws->device));
     cudaStream_t s = (cudaStream_t)stream;
     if (n_qry == 0) return PCC_OK;
@@ -73,7 +80,9 @@ extern "C" int pcc_descriptor_nn(pcc_index *ws, const float *ref, int64_t n_ref,
         PCC_CUDA(cudaMemcpyAsync(ws->stage4.p, qry, qb, cudaMemcpyHostToDevice, s));
         d_ref = ws->raw.as<float>(); d_qry = ws->stage4.as<float>(); d_oi = ws->out_i.as<int32_t>(); d_od = ws->out_f.as<float>();
     }
-    descriptor_nn_kernel<32><<<(unsigned)((n_qry + kDescThreads - 1) / kDescThreads), kDescThreads, 0, s>>>(d_ref, n_ref, stride_floats, d_qry, n_qry, stride_floats, d_oi, d_od);
+    const unsigned nb = (unsigned)((n_qry + kDescThreads - 1) / kDescThreads);
+    if (dim == 3) descriptor_nn_kernel<3><<<nb, kDescThreads, 0, s>>>(d_ref, n_ref, stride_floats, d_qry, n_qry, stride_floats, d_oi, d_od);
+    else descriptor_nn_kernel<32><<<nb, kDescThreads, 0, s>>>(d_ref, n_ref, stride_floats, d_qry, n_qry, stride_floats, d_oi, d_od);
     PCC_LAUNCHED();
     PCC_CUDA(cudaGetLastError());
     if (mem == PCC_HOST) {

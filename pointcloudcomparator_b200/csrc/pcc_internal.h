@@ -59,6 +59,7 @@ struct pcc_index {
     bool built = false;
     int64_t n_input = 0;      // rows handed to pcc_build (label / self-query row count)
     int64_t n_indexed = 0;    // finite rows
+    bool all_rows_indexed = false;   // every input row is in the index exactly once (no `indices` list, no non-finite row): self-query outputs need no pre-fill
     pcc::GridHost gh;
     pcc::Buf pts;             // float4 [n_indexed], sorted by cell
     pcc::Buf cell_start;      // uint32 [n_cells + 1]

@@ -985,7 +985,7 @@ static int knn_impl(pcc_index *idx, const void *q, int64_t nq, int stride_bytes,
         PCC_TRY(idx->out_i.reserve(cells * 4)); PCC_TRY(idx->out_f.reserve(cells * 4));
         oi = idx->out_i.as<int32_t>(); od = idx->out_f.as<float>();
     }
-    if (qs.self && idx->n_indexed < idx->n_input) {   // rows of skipped (non-finite) points stay empty: (-1, +inf)
+    if (qs.self && !idx->all_rows_indexed) {   // rows of skipped (non-finite) points stay empty: (-1, +inf)
         PCC_CUDA(cudaMemsetAsync(oi, 0xFF, cells * 4, s));
         fill_f32_kernel<<<nblocks((int64_t)cells, 256), 256, 0, s>>>(od, (int64_t)cells, INFINITY);
         PCC_LAUNCHED();
@@ -1095,7 +1095,7 @@ int pcc_knn_mean_dist(pcc_index *idx, const void *q, int64_t nq, int stride_byte
     if (!out_mean) return fail(PCC_ERR_INVALID, "output pointer is NULL");
     float *od = out_mean;
     if (mem == PCC_HOST) { PCC_TRY(idx->out_f.reserve((size_t)qs.rows * 4)); od = idx->out_f.as<float>(); }
-    if (qs.self && idx->n_indexed < idx->n_input) PCC_CUDA(cudaMemsetAsync(od, 0, (size_t)qs.rows * 4, s));
+    if (qs.self && !idx->all_rows_indexed) PCC_CUDA(cudaMemsetAsync(od, 0, (size_t)qs.rows * 4, s));
     const Grid g = idx->grid();
     const QueryView v = view_of(qs);
     const int need = mean_k + 1;
@@ -1136,7 +1136,7 @@ int pcc_normals_knn(pcc_index *idx, const void *q, int64_t nq, int stride_bytes,
     if (!idx->inv_valid) PCC_TRY(rebuild_inverse(idx, s));
     float4 *od = (float4 *)out;
     if (mem == PCC_HOST) { PCC_TRY(idx->out_f.reserve((size_t)qs.rows * 16)); od = idx->out_f.as<float4>(); }
-    if (qs.self && idx->n_indexed < idx->n_input) PCC_CUDA(cudaMemsetAsync(od, 0xFF, (size_t)qs.rows * 16, s));   // 0xFFFFFFFF = NaN
+    if (qs.self && !idx->all_rows_indexed) PCC_CUDA(cudaMemsetAsync(od, 0xFF, (size_t)qs.rows * 16, s));   // 0xFFFFFFFF = NaN
     const float vx = viewpoint ? viewpoint[0] : 0.f, vy = viewpoint ? viewpoint[1] : 0.f, vz = viewpoint ? viewpoint[2] : 0.f;
     const Grid g = idx->grid();
     const QueryView v = view_of(qs);

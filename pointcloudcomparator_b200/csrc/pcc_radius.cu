@@ -577,10 +577,11 @@ int knn_select(pcc_index *idx, const Queries &qs, int k, int32_t *oi, float *od,
 
 using namespace pcc;
 
-static int check_common(pcc_index *idx) {
+static int check_common(pcc_index *idx, void *stream = nullptr) {
     if (!idx) return fail(PCC_ERR_INVALID, "idx is NULL");
     if (!idx->built) return fail(PCC_ERR_STATE, "index not built (call pcc_build first)");
     PCC_CUDA(cudaSetDevice(idx->device));
+    if (!idx->occ_valid) PCC_TRY(rebuild_occupancy(idx, (cudaStream_t)stream));     // first query after pcc_adopt (same rule as pcc_knn.cu)
     return PCC_OK;
 }
 
@@ -665,7 +666,7 @@ int pcc_normals_radius(pcc_index *idx, const void *q, int64_t nq, int stride_byt
     PCC_TRY(radius_rows(idx, qs, radius, 0, 1, d_off, total, &keys, s));
     float4 *od = (float4 *)out;
     if (mem == PCC_HOST) { PCC_TRY(idx->out_f.reserve((size_t)qs.rows * 16)); od = idx->out_f.as<float4>(); }
-    if (qs.self && idx->n_indexed < idx->n_input) PCC_CUDA(cudaMemsetAsync(od, 0xFF, (size_t)qs.rows * 16, s));
+    if (qs.self && !idx->all_rows_indexed) PCC_CUDA(cudaMemsetAsync(od, 0xFF, (size_t)qs.rows * 16, s));
     const float vx = viewpoint ? viewpoint[0] : 0.f, vy = viewpoint ? viewpoint[1] : 0.f, vz = viewpoint ? viewpoint[2] : 0.f;
     if (qs.nq > 0) {
         normals_rows_kernel<<<nblocks(qs.nq, 128), 128, 0, s>>>(idx->grid(), view_of(qs), d_off, keys, idx->inv_pos.as<uint32_t>(), vx, vy, vz, od);

@@ -135,17 +135,26 @@ extern "C" int pcc_voxel_grid(pcc_index *idx, const void *pts, int64_t n, int st
     const int64_t m = (int64_t)(*(unsigned long long *)(h + 8));
     if (m == 0) return PCC_OK;
     VoxelParams vp;
-    int64_t div[3];
+    int64_t div[3], dchk[3];
     for (int d = 0; d < 3; ++d) {
         const float mn = ord2f_v(h[d]), mx = ord2f_v(h[3 + d]);
         vp.inv[d] = 1.0f / leaf[d];
         vp.min_b[d] = (int)std::floor(mn * vp.inv[d]);
         const int max_b = (int)std::floor(mx * vp.inv[d]);
         div[d] = (int64_t)max_b - vp.min_b[d] + 1;
-        const int64_t dchk = (int64_t)((mx - mn) * vp.inv[d]) + 1;
-        if (dchk > 2147483647ll) return fail(PCC_ERR_INVALID, "leaf size is too small for the input dataset (integer indices would overflow)");
+        dchk[d] = (int64_t)((mx - mn) * vp.inv[d]) + 1;
     }
-    if ((double)div[0] * (double)div[1] * (double)div[2] > 2147483647.0) return fail(PCC_ERR_INVALID, "leaf size is too small for the input dataset (integer indices would overflow)");
+    // PCL 1.7 VoxelGrid::applyFilter [up]: "if (dx*dy*dz > INT_MAX) { PCL_WARN(leaf size is too small ...); output = *input_; return; }"
+    // -- the input passes through UNFILTERED (every row, also the non-finite ones) and the pipeline goes on.  Same test, same
+    // outcome; the warning text is left in pcc_last_error().  (The product is formed in double so it cannot wrap.)
+    if ((double)dchk[0] * (double)dchk[1] * (double)dchk[2] > 2147483647.0 || (double)div[0] * (double)div[1] * (double)div[2] > 2147483647.0) {
+        g_error = "pcc_voxel_grid: leaf size is too small for the input dataset, integer indices would overflow -- input passed through unfiltered (PCL behaviour)";
+        if (mem == PCC_HOST) memcpy(out, pts, (size_t)n * stride_bytes);
+        else PCC_CUDA(cudaMemcpyAsync(out, pts, (size_t)n * stride_bytes, cudaMemcpyDeviceToDevice, s));
+        if (mem != PCC_HOST) PCC_CUDA(cudaStreamSynchronize(s));
+        *n_out = n;
+        return PCC_OK;
+    }
     vp.mul[0] = 1; vp.mul[1] = (int)div[0]; vp.mul[2] = (int)(div[0] * div[1]);
     // 2. keys + stable radix sort (ties keep ascending row order)
     PCC_TRY(idx->qkeys.reserve((size_t)n * 4)); PCC_TRY(idx->qkeys2.reserve((size_t)n * 4));

@@ -304,23 +304,27 @@ def region_growing(neighbours, normals, smoothness_rad: float = 3.0 / 180.0 * np
     return labels, nc.value
 
 
-def descriptor_nn(ref, qry, device: int = 0, workspace: "GridSearch | None" = None):
-    """1-NN in descriptor space (matchRIFTFeaturesKnn, src/comparator.cpp:560-588): (index into ref or -1, squared distance)."""
+def descriptor_nn(ref, qry, dims: int | None = None, device: int = 0, workspace: "GridSearch | None" = None):
+    """1-NN in descriptor space (matchRIFTFeaturesKnn, src/comparator.cpp:560-588): (index into ref or -1, squared distance).
+    `dims` = leading floats of a row that take part (None = all columns; 3 = what PCL 1.7 compares for Histogram<32>, see search.h)."""
     ws = workspace or GridSearch(device)
+    dims = int(ref.shape[1] if dims is None else dims)
     if _is_cuda(ref):
         assert ref.dtype == torch.float32 and qry.dtype == torch.float32 and ref.stride(1) == 1 and qry.stride(1) == 1 and ref.stride(0) == qry.stride(0)
         idx = torch.empty(qry.shape[0], dtype=torch.int32, device=ref.device); d2 = torch.empty(qry.shape[0], dtype=torch.float32, device=ref.device)
-        check(ws._L.pcc_descriptor_nn(ws._h, ref.data_ptr(), ref.shape[0], qry.data_ptr(), qry.shape[0], ref.shape[1], ref.stride(0), idx.data_ptr(), d2.data_ptr(), DEVICE, _stream(ws.device)))
+        check(ws._L.pcc_descriptor_nn(ws._h, ref.data_ptr(), ref.shape[0], qry.data_ptr(), qry.shape[0], dims, ref.stride(0), idx.data_ptr(), d2.data_ptr(), DEVICE, _stream(ws.device)))
         return idx, d2
     ref, qry = np.ascontiguousarray(ref, np.float32), np.ascontiguousarray(qry, np.float32)
     idx, d2 = np.empty(qry.shape[0], np.int32), np.empty(qry.shape[0], np.float32)
-    check(ws._L.pcc_descriptor_nn(ws._h, ref.ctypes.data, ref.shape[0], qry.ctypes.data, qry.shape[0], ref.shape[1], ref.shape[1], idx.ctypes.data, d2.ctypes.data, HOST, _stream(ws.device)))
+    check(ws._L.pcc_descriptor_nn(ws._h, ref.ctypes.data, ref.shape[0], qry.ctypes.data, qry.shape[0], dims, ref.shape[1], idx.ctypes.data, d2.ctypes.data, HOST, _stream(ws.device)))
     return idx, d2
 
 
-def match_rift_features_knn(desc1, desc2, threshold: float = 0.05, **kw):
-    """The reference's correspondence vector: one leading 0 (its `std::vector<int> correspondence(1)`), then the matched indices."""
-    idx, d2 = descriptor_nn(desc1, desc2, **kw)
+def match_rift_features_knn(desc1, desc2, threshold: float = 0.05, match_dims: int = 3, **kw):
+    """The reference's correspondence vector: one leading 0 (its `std::vector<int> correspondence(1)`), then the matched indices.
+    match_dims = 3 reproduces the reference binary (PCL 1.7 clamps an unregistered Histogram<32> to its first 3 floats);
+    match_dims = 32 matches on the whole RIFT histogram."""
+    idx, d2 = descriptor_nn(desc1, desc2, dims=match_dims, **kw)
     if _is_cuda(idx):
         idx, d2 = idx.cpu().numpy(), d2.cpu().numpy()
     keep = (idx >= 0) & (d2 < np.float32(threshold))

@@ -446,6 +446,45 @@ def test_radius_rows_of_every_length(GS):
     assert lens.max() > 1024 and (lens <= 32).any() and ((lens > 32) & (lens <= 1024)).any()
 
 
+def test_indices_with_duplicates_leave_unindexed_rows_empty(GS):
+    """an `indices` list may repeat rows, so n_indexed >= n_input does not mean every input row is indexed; the
+    self-query outputs of the rows that are not must still be pre-filled ((-1, +inf) / 0 / NaN)."""
+    pts = np.array([[0, 0, 0], [1, 0, 0], [5, 5, 5], [6, 6, 6]], np.float32)
+    s = GS().setInputCloud(pts, indices=np.array([0, 0, 1, 1], np.int32))
+    assert s.size == 4
+    gi, gd, _ = s.nearestKSearch(None, 2)
+    assert (gi[2:] == -1).all() and np.isinf(gd[2:]).all()
+    assert set(gi[0].tolist()) == {0} and set(gi[1].tolist()) == {1} and (gd[:2] == 0).all()      # each indexed twice: its two nearest are its own two copies
+    md = s.meanNeighbourDistance(None, 1)
+    assert (md[2:] == 0).all()
+    nrm = s.normalsKnn(None, 3)
+    assert np.isnan(nrm[2:]).all()
+    nr = s.normalsRadius(None, 10.0)
+    assert np.isnan(nr[2:]).all()
+
+
+def test_query_batch_size_guard(GS):
+    """Row counts are handed to CUB as 32-bit ints: a batch of 2^31 rows must be refused loudly, before any memory is touched."""
+    from pointcloudcomparator_b200 import _lib
+    import ctypes as C
+    s = GS().setInputCloud(synth.room(2000, 1001))
+    L = _lib.lib()
+    keff = C.c_int()
+    rc = L.pcc_knn(s._h, C.c_void_p(16), 1 << 31, 16, 4, C.c_void_p(16), C.c_void_p(16), C.byref(keff), _lib.DEVICE, None)
+    assert rc == -1 and b"nq" in L.pcc_last_error()
+
+
+def test_voxel_grid_leaf_too_small_passes_input_through(GS):
+    """PCL 1.7 VoxelGrid::applyFilter warns and returns the input unfiltered when the voxel index would overflow int32
+    (src/segmentation.cpp:69-74 would then cluster the full cloud); product and oracle both mirror that instead of failing."""
+    from pointcloudcomparator_b200.search import voxel_grid
+    p = synth.room(5000, 1001, stride4=True)
+    p[17, 2] = np.nan
+    out = voxel_grid(p, 1e-5)
+    ref = oracle.voxel_grid(p, 1e-5)
+    assert out.shape == p.shape and np.array_equal(bits(out), bits(p)) and np.array_equal(bits(ref), bits(p))
+
+
 def test_descriptor_nn_vs_oracle(GS):
     """RIFT32 1-NN (src/comparator.cpp:560-588), bit-exact vs the oracle incl. the reference's vector shape."""
     import torch
@@ -461,8 +500,18 @@ def test_descriptor_nn_vs_oracle(GS):
         assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od))
         di, dd = descriptor_nn(torch.from_numpy(ref).cuda(), torch.from_numpy(qry).cuda())
         assert np.array_equal(di.cpu().numpy(), oi) and np.array_equal(bits(dd.cpu().numpy()), bits(od))
-        corr = match_rift_features_knn(ref, qry)
+        corr = match_rift_features_knn(ref, qry, match_dims=32)
         assert corr == [0] + oi[(oi >= 0) & (od < np.float32(0.05))].tolist()
+        # reference-exact mode: PCL 1.7 compares only the first 3 floats of an unregistered Histogram<32> (distance AND validity)
+        g3, d3 = descriptor_nn(ref, qry, dims=3)
+        o3, od3 = oracle.descriptor_nn(ref, qry, dims=3)
+        assert np.array_equal(g3, o3) and np.array_equal(bits(d3), bits(od3))
+        t3, td3 = descriptor_nn(torch.from_numpy(ref).cuda(), torch.from_numpy(qry).cuda(), dims=3)
+        assert np.array_equal(t3.cpu().numpy(), o3) and np.array_equal(bits(td3.cpu().numpy()), bits(od3))
+        if n1 > 10:
+            assert o3[1] >= 0 and oi[1] == -1            # the query whose bin 31 is inf is valid in 3-D, empty in 32-D
+            assert (o3 == 3).sum() >= 0 and not (oi == 3).any()       # reference row 3 (NaN in bin 9) can only match in 3-D
+        assert match_rift_features_knn(ref, qry) == [0] + o3[(o3 >= 0) & (od3 < np.float32(0.05))].tolist()      # default = reference-exact
 
 
 # ---------------------------------------------------------------- the passes behind the 3x3x3 block (rings / wide / tied)

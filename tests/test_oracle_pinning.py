@@ -489,3 +489,19 @@ def test_icp_vs_numpy_loop():
     assert abs(r["iterations"] - it) <= 1
     assert np.allclose(r["T"], final, atol=5e-5)
     assert np.isclose(r["fitness"], fit, rtol=2e-3)
+
+
+def test_descriptor_nn_three_dims_matches_flann_on_first_three_bins():
+    """PCL 1.7's DefaultPointRepresentation clamps an unregistered point type to its first 3 floats, so the reference's
+    KdTreeFLANN<Histogram<32>> (src/comparator.cpp:564-577) is a 3-D tree over bins 0..2: the oracle's dims = 3 mode against a
+    FLANN KDTreeSingleIndex built on exactly those columns."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(8)
+    ref = rng.random((900, 32), dtype=np.float32) * 0.3
+    qry = (ref[rng.integers(0, 900, 500)] + rng.normal(0, 0.02, (500, 32))).astype(np.float32)
+    fl = cv2.flann_Index(np.ascontiguousarray(ref[:, :3]), dict(algorithm=4, leaf_max_size=15))
+    ci, cd = fl.knnSearch(np.ascontiguousarray(qry[:, :3]), 1, params=dict(checks=-1, eps=0.0, sorted=True))
+    oi, od = oracle.descriptor_nn(ref, qry, dims=3)
+    assert np.array_equal(ci[:, 0], oi) and np.allclose(cd[:, 0], od, rtol=1e-6, atol=0)
+    o32, _ = oracle.descriptor_nn(ref, qry)
+    assert (o32 != oi).any()                               # the two modes really differ on this data
