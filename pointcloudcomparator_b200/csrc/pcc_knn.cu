@@ -30,6 +30,12 @@ __device__ __forceinline__ bool load_query(const Grid &g, const QueryView &v, in
     if (v.self) { float4 p = __ldg(g.pts + t); x = p.x; y = p.y; z = p.z; row = __float_as_int(p.w); return true; }
     uint32_t qi = v.order ? __ldg(v.order + t) : (uint32_t)t;
     float4 p = __ldg(v.q + qi); x = p.x; y = p.y; z = p.z; row = qi;
+#ifdef PCC_EXP_SEQROWS        // measurement build only (results land in processing order): what do the scattered 128-byte row writes cost?
+    row = t;
+#endif
+#ifdef PCC_EXP_SEQQ           // measurement build only: queries read in processing order instead of gathered through `order`
+    p = __ldg(v.q + t); x = p.x; y = p.y; z = p.z;
+#endif
     if (!finite3(x, y, z) || g.n == 0) { write_empty = true; return false; }
     return true;
 }

@@ -195,7 +195,7 @@ __device__ __forceinline__ void prefetch_run(const float4 *pts, uint32_t j, uint
     if (L1) prefetch_l1(last); else prefetch_l2(last);
 }
 #ifndef PCC_THR_PIPE
-#define PCC_THR_PIPE 1
+#define PCC_THR_PIPE 0
 #endif
 struct Quad { float4 p0, p1, p2, p3; };
 __device__ __forceinline__ Quad load_quad(const float4 *__restrict__ pts, uint32_t j) { Quad q; q.p0 = __ldg(pts + j); q.p1 = __ldg(pts + j + 1); q.p2 = __ldg(pts + j + 2); q.p3 = __ldg(pts + j + 3); return q; }
@@ -210,9 +210,9 @@ __device__ __forceinline__ void thr_quad(const Quad &q, const uint32_t j, const 
     if (!COMPRESS) wa = min(wa, cap);
     else if (wa >= cap) on_full();                        // not clamped first: the entries in the sacrificial slots are real
 }
-// Software-pipelined: the four loads of step i+1 are issued before step i is processed (two register sets, loop unrolled by two), so
-// a warp keeps eight 16-byte loads in flight.  Measured motivation: with 4 warps per scheduler and one step in flight per warp, the
-// L2 round trip of a step (43 % of the sectors miss the small L1 left beside 192 KB of logs) was exposed on nearly every step.
+// PCC_THR_PIPE = 1 software-pipelines the walk (the four loads of step i+1 are issued before step i is processed, two register
+// sets, loop unrolled by two).  Measured on B200: no gain (3.62 vs 3.51 ms for the stage, and the retry kernel doubles) -- the
+// exposed time is not the latency of one step's loads (profiles/r2/blockkernel_load_experiments.txt), so it is off by default.
 template <uint32_t STRIDE, bool COMPRESS, class F>
 __device__ __forceinline__ void thr_walk_run(const Grid &g, uint32_t j, const uint32_t e, const float x, const float y, const float z, float &T,
                                              float &dmin, float &tau, uint32_t &wa, const uint32_t cap, F &&on_full) {
