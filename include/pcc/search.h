@@ -148,6 +148,17 @@ int pcc_voxel_grid(pcc_index *idx, const void *pts, int64_t n, int stride_bytes,
 int pcc_region_growing(const int32_t *neighbours, int64_t n, int k, const float *normals4, float smoothness_rad, float curvature_threshold,
                        int64_t min_size, int64_t max_size, int32_t *labels, int64_t *n_clusters);
 
+/* RegionGrowingRGB::extract minus findPointNeighbours (color_growing_segmentation, src/segmentation.cpp:161-216, run on both clouds of
+ * every matched cluster pair at src/comparator.cpp:1457-1460, which then compares the cluster COUNTS) [up]: colour grow over the
+ * N x k table of pcc_knn(q == NULL, k = 100) and its squared distances, segment neighbours, merge by mean colour, fold small regions,
+ * size filter.  HOST pointers (sequential, order-dependent).  rgba = one packed 0x00RRGGBB word per point (PCL's PointXYZRGB::rgba),
+ * rgba_stride_bytes apart.  Reference configuration: distance 10, point colour 6, region colour 5, min size 200, max INT_MAX;
+ * grow_neighbours = 30 (RegionGrowing::neighbour_number_, which the reference never sets: growRegion only walks the first 30 of
+ * the 100 neighbours).  labels[i] = cluster number in PCL's order, or -1. */
+int pcc_region_growing_rgb(const int32_t *neighbours, const float *sqr_distances, int64_t n, int k, const uint32_t *rgba, int rgba_stride_bytes,
+                           float distance_threshold, float point_color_threshold, float region_color_threshold, int grow_neighbours,
+                           int64_t min_size, int64_t max_size, int32_t *labels, int64_t *n_clusters);
+
 /* matchRIFTFeaturesKnn (src/comparator.cpp:560-588): KdTreeFLANN<Histogram<32>> over `ref`, nearestKSearch(k = 1) for every row
  * of `qry` [up].  Exact brute force in descriptor space: d2 accumulated sequentially over the first `dim` floats of a row (fp32, no
  * FMA), ties to the lowest index, reference rows that are non-finite in those floats skipped, such queries get (-1, +inf).  The

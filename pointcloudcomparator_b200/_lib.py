@@ -22,7 +22,7 @@ SYMBOLS = [
     "pcc_knn", "pcc_radius_count", "pcc_radius_fill", "pcc_knn_mean_dist", "pcc_sor_threshold", "pcc_normals_knn",
     "pcc_normals_radius", "pcc_icp_step", "pcc_icp_align", "pcc_umeyama_from_sums", "pcc_euclidean_labels", "pcc_first_within",
     "pcc_export", "pcc_adopt", "pcc_set_timing", "pcc_last_kernel_ms", "pcc_ece_init", "pcc_ece_link_range", "pcc_ece_absorb", "pcc_ece_finish", "pcc_voxel_grid", "pcc_descriptor_nn", "pcc_region_growing",
-    "pcc_comm_init", "pcc_comm_info", "pcc_broadcast_index", "pcc_gather", "pcc_allreduce_f64",
+    "pcc_region_growing_rgb", "pcc_comm_init", "pcc_comm_info", "pcc_broadcast_index", "pcc_gather", "pcc_allreduce_f64",
 ]
 
 
@@ -69,6 +69,7 @@ def lib():
     L.pcc_region_growing.argtypes = [vp, i64, i32, vp, C.c_float, C.c_float, i64, i64, vp, C.POINTER(i64)]
     L.pcc_export.argtypes = [vp, C.POINTER(dbl), C.POINTER(vp)]
     L.pcc_adopt.argtypes = [vp, C.POINTER(dbl), vp]
+    L.pcc_region_growing_rgb.argtypes = [vp, vp, i64, i32, vp, i32, C.c_float, C.c_float, C.c_float, i32, i64, i64, vp, C.POINTER(i64)]
     L.pcc_comm_init.argtypes = [vp, vp, i32, i32]
     L.pcc_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     L.pcc_broadcast_index.argtypes = [vp, i32, vp]

@@ -1,6 +1,8 @@
 // pcc_consumers.cu -- the O(1)/O(n) host-driven parts of the consumers: StatisticalOutlierRemoval's second pass,
 // Umeyama from the ICP sums, and the ICP loop itself.
 #include <algorithm>
+#include <array>
+#include <limits>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -214,6 +216,146 @@ int pcc_region_growing(const int32_t *neighbours, int64_t n, int k, const float 
     int64_t kept = 0;
     for (size_t s2 = 0; s2 < seg_size.size(); ++s2) if (seg_size[s2] >= min_size && seg_size[s2] <= max_size) rank[s2] = (int32_t)kept++;
     for (int64_t i = 0; i < n; ++i) labels[i] = rank[(size_t)seg[(size_t)i]];
+    *n_clusters = kept;
+    return PCC_OK;
+}
+
+// RegionGrowingRGB::extract minus findPointNeighbours (src/segmentation.cpp:179-190, called per matched cluster at
+// src/comparator.cpp:1457-1460; the consumer only counts the clusters that come out) [up: segmentation/impl/region_growing_rgb.hpp
+// and region_growing.hpp of PCL 1.7, restated from the published source -- NOT in /root/reference, see DESIGN.md]:
+//   1. grow (RegionGrowing::applySmoothRegionGrowingAlgorithm with RegionGrowingRGB::validatePoint): normals are off in the
+//      reference's configuration, so seeds are taken in index order; a neighbour joins when its colour is within
+//      point_color_threshold of the CURRENT point (squared RGB distance > thr^2 rejects) and always becomes a seed.  growRegion only
+//      walks the first `grow_neighbours` (RegionGrowing's neighbour_number_, 30 unless set) of the k = 100 neighbours
+//      RegionGrowingRGB::findPointNeighbours asks for;
+//   2. findSegmentNeighbours / findRegionsKNN: for every segment the nearest other segments by the smallest neighbour-table distance
+//      (squared, as the search returns it) between their points, the k nearest kept, listed farthest first (a std::priority_queue);
+//   3. applyRegionMergingAlgorithm: mean colour per segment (unsigned sums, float division, truncation); in segment order, neighbours
+//      within distance_threshold^2 whose mean colour is within region_color_threshold^2 (strict <) join the homogeneous region;
+//      then regions smaller than min_size are folded into their nearest neighbouring region;
+//   4. assembleRegions + the size filter of extract().  labels[i] = cluster number in PCL's final order, or -1.
+// Sequential and order-dependent like the plain RegionGrowing grow phase, hence host code over the GPU-built N x k table.
+int pcc_region_growing_rgb(const int32_t *neighbours, const float *sqr_distances, int64_t n, int k, const uint32_t *rgba, int rgba_stride_bytes,
+                           float distance_threshold, float point_color_threshold, float region_color_threshold, int grow_neighbours,
+                           int64_t min_size, int64_t max_size, int32_t *labels, int64_t *n_clusters) {
+    if (n < 0 || k < 1 || (n > 0 && (!neighbours || !sqr_distances || !rgba || !labels)) || !n_clusters || rgba_stride_bytes < 4 || (rgba_stride_bytes & 3) || grow_neighbours < 1)
+        return fail(PCC_ERR_INVALID, "bad arguments");
+    *n_clusters = 0;
+    if (n == 0) return PCC_OK;
+    const float dist_thr = distance_threshold * distance_threshold, p2p = point_color_threshold * point_color_threshold, r2r = region_color_threshold * region_color_threshold;
+    auto colour = [&](int64_t i, unsigned c[3]) { const uint32_t v = *(const uint32_t *)((const uint8_t *)rgba + (size_t)i * rgba_stride_bytes); c[0] = (v >> 16) & 255u; c[1] = (v >> 8) & 255u; c[2] = v & 255u; };
+    auto colour_diff = [](const unsigned a[3], const unsigned b[3]) {       // calculateColorimetricalDifference: unsigned products, summed in float
+        float d = 0.f;
+        d += (float)((a[0] - b[0]) * (a[0] - b[0])); d += (float)((a[1] - b[1]) * (a[1] - b[1])); d += (float)((a[2] - b[2]) * (a[2] - b[2]));
+        return d;
+    };
+    auto row_len = [&](int64_t i) { int m = 0; const int32_t *r = neighbours + (size_t)i * k; while (m < k && r[m] >= 0) ++m; return m; };
+    // 1. grow
+    std::vector<int32_t> point_label((size_t)n, -1), queue;
+    std::vector<int64_t> seg_size;
+    for (int64_t seed0 = 0; seed0 < n; ++seed0) {
+        if (point_label[(size_t)seed0] != -1) continue;
+        const int32_t s_id = (int32_t)seg_size.size();
+        int64_t count = 1;
+        point_label[(size_t)seed0] = s_id;
+        queue.clear(); queue.push_back((int32_t)seed0);
+        for (size_t head = 0; head < queue.size(); ++head) {
+            const int32_t cur = queue[head];
+            unsigned cc[3]; colour(cur, cc);
+            const int32_t *nb = neighbours + (size_t)cur * k;
+            const int lim = std::min(grow_neighbours, row_len(cur));
+            for (int j = 0; j < lim; ++j) {
+                const int32_t q = nb[j];
+                if (point_label[(size_t)q] != -1) continue;
+                unsigned nc[3]; colour(q, nc);
+                if (colour_diff(cc, nc) > p2p) continue;
+                point_label[(size_t)q] = s_id; ++count;
+                queue.push_back(q);
+            }
+        }
+        seg_size.push_back(count);
+    }
+    const int n_seg = (int)seg_size.size();
+    std::vector<std::vector<int32_t>> seg_pts((size_t)n_seg);
+    for (int sg = 0; sg < n_seg; ++sg) seg_pts[(size_t)sg].reserve((size_t)seg_size[(size_t)sg]);
+    for (int64_t i = 0; i < n; ++i) seg_pts[(size_t)point_label[(size_t)i]].push_back((int32_t)i);
+    // 2. segment neighbours (findRegionsKNN for every segment)
+    std::vector<std::vector<int>> seg_nb((size_t)n_seg);
+    std::vector<std::vector<float>> seg_nd((size_t)n_seg);
+    {
+        const float max_dist = std::numeric_limits<float>::max();
+        std::vector<float> dist((size_t)n_seg, max_dist);
+        std::vector<int> stamp((size_t)n_seg, -1), touched;
+        std::vector<std::pair<float, int>> cand;
+        for (int sg = 0; sg < n_seg; ++sg) {
+            touched.clear();
+            for (int32_t p : seg_pts[(size_t)sg]) {
+                const int32_t *nb = neighbours + (size_t)p * k; const float *nd = sqr_distances + (size_t)p * k;
+                const int m = row_len(p);
+                for (int j = 0; j < m; ++j) {
+                    const int os = point_label[(size_t)nb[j]];
+                    if (os == sg) continue;
+                    if (stamp[(size_t)os] != sg) { stamp[(size_t)os] = sg; dist[(size_t)os] = max_dist; touched.push_back(os); }
+                    if (dist[(size_t)os] > nd[j]) dist[(size_t)os] = nd[j];
+                }
+            }
+            // PCL pushes (distance, segment) into a std::priority_queue and pops its maximum whenever it holds more than k: the k
+            // smallest pairs survive (lexicographic), and they are then popped farthest first
+            cand.clear();
+            for (int os : touched) if (dist[(size_t)os] < max_dist) cand.push_back(std::make_pair(dist[(size_t)os], os));
+            std::sort(cand.begin(), cand.end());
+            if ((int)cand.size() > k) cand.resize((size_t)k);
+            for (size_t c = cand.size(); c-- > 0;) { seg_nd[(size_t)sg].push_back(cand[c].first); seg_nb[(size_t)sg].push_back(cand[c].second); }
+        }
+    }
+    // 3. merge by mean colour
+    std::vector<std::array<unsigned, 3>> seg_col((size_t)n_seg, std::array<unsigned, 3>{0u, 0u, 0u});
+    for (int64_t i = 0; i < n; ++i) { unsigned c[3]; colour(i, c); auto &a = seg_col[(size_t)point_label[(size_t)i]]; a[0] += c[0]; a[1] += c[1]; a[2] += c[2]; }
+    for (int sg = 0; sg < n_seg; ++sg) for (int c = 0; c < 3; ++c) seg_col[(size_t)sg][c] = (unsigned)((float)seg_col[(size_t)sg][c] / (float)seg_size[(size_t)sg]);
+    std::vector<int> seg_label((size_t)n_seg, -1);
+    std::vector<int64_t> reg_pts; std::vector<int> reg_segs;
+    for (int sg = 0; sg < n_seg; ++sg) {
+        int cur;
+        if (seg_label[(size_t)sg] == -1) { seg_label[(size_t)sg] = cur = (int)reg_pts.size(); reg_pts.push_back(seg_size[(size_t)sg]); reg_segs.push_back(1); }
+        else cur = seg_label[(size_t)sg];
+        for (size_t j = 0; j < seg_nb[(size_t)sg].size() && (int)j < k; ++j) {
+            const int os = seg_nb[(size_t)sg][j];
+            if (seg_nd[(size_t)sg][j] > dist_thr) continue;
+            if (seg_label[(size_t)os] != -1) continue;
+            if (colour_diff(seg_col[(size_t)sg].data(), seg_col[(size_t)os].data()) < r2r) { seg_label[(size_t)os] = cur; reg_pts[(size_t)cur] += seg_size[(size_t)os]; reg_segs[(size_t)cur] += 1; }
+        }
+    }
+    const int n_reg = (int)reg_pts.size();
+    std::vector<std::vector<int>> final_segs((size_t)n_reg);
+    for (int sg = 0; sg < n_seg; ++sg) final_segs[(size_t)seg_label[(size_t)sg]].push_back(sg);
+    // findRegionNeighbours: per region the (distance, segment) pairs of its segments' neighbours that lie in other regions, ascending by distance
+    auto by_first = [](const std::pair<float, int> &a, const std::pair<float, int> &b) { return a.first < b.first; };
+    std::vector<std::vector<std::pair<float, int>>> reg_nb((size_t)n_reg);
+    for (int r = 0; r < n_reg; ++r) {
+        for (int sg : final_segs[(size_t)r])
+            for (size_t j = 0; j < seg_nb[(size_t)sg].size(); ++j)
+                if (seg_label[(size_t)seg_nb[(size_t)sg][j]] != r) reg_nb[(size_t)r].push_back(std::make_pair(seg_nd[(size_t)sg][j], seg_nb[(size_t)sg][j]));
+        std::stable_sort(reg_nb[(size_t)r].begin(), reg_nb[(size_t)r].end(), by_first);
+    }
+    for (int r = 0; r < n_reg; ++r) {
+        if (reg_pts[(size_t)r] >= min_size) continue;
+        if (reg_nb[(size_t)r].empty()) continue;
+        if (reg_nb[(size_t)r][0].first == std::numeric_limits<float>::max()) continue;
+        const int target = seg_label[(size_t)reg_nb[(size_t)r][0].second];
+        for (int sg : final_segs[(size_t)r]) { final_segs[(size_t)target].push_back(sg); seg_label[(size_t)sg] = target; }
+        final_segs[(size_t)r].clear();
+        reg_pts[(size_t)target] += reg_pts[(size_t)r]; reg_pts[(size_t)r] = 0;
+        reg_segs[(size_t)target] += reg_segs[(size_t)r]; reg_segs[(size_t)r] = 0;
+        for (auto &pr : reg_nb[(size_t)target]) if (seg_label[(size_t)pr.second] == target) { pr.first = std::numeric_limits<float>::max(); pr.second = 0; }
+        for (const auto &pr : reg_nb[(size_t)r]) if (seg_label[(size_t)pr.second] != target) reg_nb[(size_t)target].push_back(pr);
+        reg_nb[(size_t)r].clear();
+        std::stable_sort(reg_nb[(size_t)target].begin(), reg_nb[(size_t)target].end(), by_first);
+    }
+    // 4. assembleRegions (empty regions erased, order kept) + extract()'s size filter
+    std::vector<int32_t> rank((size_t)n_reg, -1);
+    int64_t kept = 0;
+    for (int r = 0; r < n_reg; ++r) if (reg_pts[(size_t)r] > 0 && reg_pts[(size_t)r] >= min_size && reg_pts[(size_t)r] <= max_size) rank[(size_t)r] = (int32_t)kept++;
+    for (int64_t i = 0; i < n; ++i) labels[i] = rank[(size_t)seg_label[(size_t)point_label[(size_t)i]]];
     *n_clusters = kept;
     return PCC_OK;
 }

@@ -304,6 +304,21 @@ def region_growing(neighbours, normals, smoothness_rad: float = 3.0 / 180.0 * np
     return labels, nc.value
 
 
+def region_growing_rgb(neighbours, sqr_distances, rgba, distance_threshold: float = 10.0, point_color_threshold: float = 6.0, region_color_threshold: float = 5.0,
+                       grow_neighbours: int = 30, min_size: int = 200, max_size: int = 2**31 - 1):
+    """RegionGrowingRGB::extract over the GPU-built N x k table (color_growing_segmentation, src/segmentation.cpp:161-216): returns
+    (labels[n] int32, n_clusters).  rgba = packed 0x00RRGGBB words (uint32[n])."""
+    nb = np.ascontiguousarray(neighbours, np.int32)
+    nd = np.ascontiguousarray(sqr_distances, np.float32)
+    col = np.ascontiguousarray(rgba, np.uint32)
+    assert nb.shape == nd.shape and col.shape[0] == nb.shape[0]
+    labels = np.empty(nb.shape[0], np.int32)
+    nc = C.c_int64()
+    check(_lib.lib().pcc_region_growing_rgb(nb.ctypes.data, nd.ctypes.data, nb.shape[0], nb.shape[1], col.ctypes.data, 4, float(distance_threshold), float(point_color_threshold),
+                                            float(region_color_threshold), int(grow_neighbours), int(min_size), int(max_size), labels.ctypes.data, C.byref(nc)))
+    return labels, int(nc.value)
+
+
 def descriptor_nn(ref, qry, dims: int | None = None, device: int = 0, workspace: "GridSearch | None" = None):
     """1-NN in descriptor space (matchRIFTFeaturesKnn, src/comparator.cpp:560-588): (index into ref or -1, squared distance).
     `dims` = leading floats of a row that take part (None = all columns; 3 = what PCL 1.7 compares for Histogram<32>, see search.h)."""

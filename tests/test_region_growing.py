@@ -80,3 +80,86 @@ def test_region_growing_known_answer_two_perpendicular_planes():
         lab, nc = fn(nbr, normals, 3.0 / 180 * np.pi, 1.0, 50, 100000)
         assert nc == 2
         assert (lab[: len(floor)] == 0).all() and (lab[len(floor):] == 1).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# RegionGrowingRGB (color_growing_segmentation, src/segmentation.cpp:161-216; per matched cluster at src/comparator.cpp:1457-1460)
+
+def _coloured_patches(n, seed, n_patches=6, jitter=2, speckle=0.0):
+    """A flat 1 x 1 m patch-work: vertical stripes of distinct base colours (+- jitter per channel) and optional random speckle."""
+    rng = np.random.default_rng(seed)
+    p = np.zeros((n, 3), np.float32)
+    p[:, :2] = rng.random((n, 2))
+    base = rng.integers(30, 226, (n_patches, 3))
+    stripe = np.minimum((p[:, 0] * n_patches).astype(int), n_patches - 1)
+    col = np.clip(base[stripe] + rng.integers(-jitter, jitter + 1, (n, 3)), 0, 255)
+    sp = rng.random(n) < speckle
+    col[sp] = rng.integers(0, 256, (int(sp.sum()), 3))
+    rgba = (col[:, 0].astype(np.uint32) << 16) | (col[:, 1].astype(np.uint32) << 8) | col[:, 2].astype(np.uint32)
+    return p, rgba, stripe
+
+
+def _table(p, k):
+    idx, d2, _ = oracle.KdTree(p).knn(p, k)
+    return idx, d2
+
+
+def test_region_growing_rgb_matches_python_oracle_reference_configuration():
+    from oracle import rgb_region_growing
+    from pointcloudcomparator_b200.search import region_growing_rgb
+    p, rgba, stripe = _coloured_patches(6000, 3, n_patches=5, jitter=1)
+    nb, nd = _table(p, 100)
+    lab, nc = region_growing_rgb(nb, nd, rgba)                               # distance 10, point colour 6, region colour 5, min 200
+    olab, onc = rgb_region_growing.extract(nb, nd, rgba)
+    assert nc == onc and np.array_equal(lab, olab)
+    assert nc == 5                                                            # one cluster per stripe: the known answer
+    for s in range(5):
+        assert len(set(lab[stripe == s].tolist())) == 1
+
+
+@pytest.mark.parametrize("jitter,speckle,pthr,rthr,dthr,mn,grow", [(4, 0.0, 6.0, 5.0, 10.0, 200, 30), (3, 0.05, 6.0, 5.0, 10.0, 50, 30), (6, 0.02, 9.0, 12.0, 0.02, 20, 10),
+                                                              (2, 0.10, 4.0, 40.0, 10.0, 400, 100)])
+def test_region_growing_rgb_parameter_sweep(jitter, speckle, pthr, rthr, dthr, mn, grow):
+    """Speckle makes hundreds of tiny segments, so the neighbour heaps, the colour merge and the fold of small regions all run."""
+    from oracle import rgb_region_growing
+    from pointcloudcomparator_b200.search import region_growing_rgb
+    p, rgba, _ = _coloured_patches(3000, 11 + jitter, n_patches=7, jitter=jitter, speckle=speckle)
+    nb, nd = _table(p, 40)
+    a = region_growing_rgb(nb, nd, rgba, dthr, pthr, rthr, grow, mn)
+    b = rgb_region_growing.extract(nb, nd, rgba, dthr, pthr, rthr, grow, None, mn)
+    assert a[1] == b[1] and np.array_equal(a[0], b[0])
+    assert (np.bincount(a[0][a[0] >= 0]) >= mn).all() if a[1] else True
+
+
+def test_region_growing_rgb_small_known_answers():
+    from pointcloudcomparator_b200.search import region_growing_rgb
+    # four points on a line, two colours; k = 3; everything within distance 10 -> colours decide
+    nb = np.array([[0, 1, 2], [1, 0, 2], [2, 3, 1], [3, 2, 1]], np.int32)
+    nd = np.array([[0, 1, 4], [0, 1, 1], [0, 1, 1], [0, 1, 4]], np.float32)
+    red, blue = 0xC80000, 0x0000C8
+    lab, nc = region_growing_rgb(nb, nd, np.array([red, red, blue, blue], np.uint32), 10.0, 6.0, 5.0, 30, 1)
+    assert nc == 2 and lab.tolist() == [0, 0, 1, 1]
+    # min size 3: each 2-point region folds into its neighbour -> one cluster of 4
+    lab, nc = region_growing_rgb(nb, nd, np.array([red, red, blue, blue], np.uint32), 10.0, 6.0, 5.0, 30, 3)
+    assert nc == 1 and lab.tolist() == [0, 0, 0, 0]
+    # a colour step of exactly the point threshold is accepted (PCL rejects on ">"): 6^2 = 36 = (6, 0, 0) squared
+    lab, nc = region_growing_rgb(nb, nd, np.array([0x640000, 0x6A0000, 0x700000, 0x760000], np.uint32), 10.0, 6.0, 5.0, 30, 1)
+    assert nc == 1
+    lab, nc = region_growing_rgb(nb, nd, np.array([0x640000, 0x6B0000, 0x720000, 0x790000], np.uint32), 10.0, 6.0, 0.5, 30, 1)
+    assert nc == 4
+
+
+@pytest.mark.gpu
+def test_region_growing_rgb_on_gpu_table():
+    """The N x 100 table and its squared distances come from the GPU (pcc_knn with q == NULL); clusters must equal the oracle's on
+    the oracle's own table, i.e. the table is bit-exact and the host grow / merge agrees."""
+    from oracle import rgb_region_growing
+    from pointcloudcomparator_b200.search import GridSearch, region_growing_rgb
+    p, rgba, _ = _coloured_patches(5000, 21, n_patches=4, jitter=2, speckle=0.01)
+    s = GridSearch().setInputCloud(p, k_hint=100)
+    nb, nd, _ = s.nearestKSearch(None, 100)
+    onb, ond = _table(p, 100)
+    assert np.array_equal(nb, onb) and np.array_equal(nd.view(np.uint32), ond.view(np.uint32))
+    lab, nc = region_growing_rgb(nb, nd, rgba)
+    olab, onc = rgb_region_growing.extract(onb, ond, rgba)
+    assert nc == onc and np.array_equal(lab, olab)
