@@ -192,12 +192,13 @@ def test_normals_knn_vs_oracle(GS):
     s = GS().setInputCloud(ref, k_hint=50)
     n = s.normalsKnn(None, 50)
     o = oracle.normals_knn(ref, 50)
-    # eigen33 uses atan2f/cosf/sinf whose last-ulp rounding differs between glibc and CUDA; tolerance 1e-5 (north_star)
-    # on the unit normal, except where the smallest eigenvalue is (near-)degenerate and the eigenvector is ill-conditioned.
+    # eigen33 uses atan2f/cosf/sinf whose last-ulp rounding differs between glibc and CUDA; north_star's tolerance is 1e-5 on the unit
+    # normal and EVERY point must meet it (measured on B200: max 3.0e-7 over all 60000 points, gap (l1 - l0) / max|cov| >= 0.27 for 99 %
+    # of them -- profiles/r2/normals_error_vs_gap.txt); the oracle's own eigen33 is pinned against LAPACK in test_oracle_pinning.py.
     err = _normal_err(n, o)
     assert np.isfinite(n).all()
-    assert np.quantile(err, 0.99) < 1e-5 and (err < 1e-5).mean() > 0.995
-    assert np.allclose(n[:, 3], o[:, 3], rtol=1e-4, atol=1e-6)
+    assert err.max() < 1e-5, err.max()
+    assert np.allclose(n[:, 3], o[:, 3], rtol=1e-3, atol=5e-7)           # curvature = |l0 / trace|: absolute error 8e-8 measured; tiny curvatures make the relative one meaningless
     assert (np.einsum("ij,ij->i", -ref[:, :3], n[:, :3]) >= -1e-6).all()   # flipped towards the viewpoint (origin)
 
 
@@ -209,7 +210,8 @@ def test_normals_radius_and_degenerate(GS):
     assert np.array_equal(np.isnan(n[:, 0]), np.isnan(o[:, 0]))             # < 3 neighbours -> NaN on both sides
     ok = ~np.isnan(o[:, 0])
     err = _normal_err(n[ok], o[ok])
-    assert np.quantile(err, 0.98) < 1e-5
+    assert err.max() < 1e-5, err.max()                                      # every normal, also the ill-conditioned 3- and 4-point neighbourhoods (measured max 2.0e-7)
+    assert np.allclose(n[ok, 3], o[ok, 3], rtol=1e-3, atol=5e-7)
     lone = np.array([[0, 0, 0], [5, 5, 5]], np.float32)
     assert np.isnan(GS().setInputCloud(lone).normalsRadius(None, 0.1)).all()
 
