@@ -202,8 +202,11 @@ int prepare_queries(pcc_index *idx, const void *q, int64_t nq, int stride_bytes,
     out->order = nullptr;
     if (sort) {
         int bits = 1; while ((1ll << bits) <= idx->gh.n_cells && bits < 32) ++bits;
-        size_t tmp = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp, idx->qkeys.as<uint32_t>(), idx->qkeys2.as<uint32_t>(), idx->qperm.as<uint32_t>(), idx->qperm2.as<uint32_t>(), (int)nq, 0, bits, s);
+        size_t tmp = idx->sort_tmp_bytes;
+        if (idx->sort_tmp_nq != nq || idx->sort_tmp_bits != bits) {
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp, idx->qkeys.as<uint32_t>(), idx->qkeys2.as<uint32_t>(), idx->qperm.as<uint32_t>(), idx->qperm2.as<uint32_t>(), (int)nq, 0, bits, s);
+            idx->sort_tmp_nq = nq; idx->sort_tmp_bits = bits; idx->sort_tmp_bytes = tmp;
+        }
         PCC_TRY(idx->cub_tmp.reserve(tmp));
         PCC_CUDA(cub::DeviceRadixSort::SortPairs(idx->cub_tmp.p, tmp, idx->qkeys.as<uint32_t>(), idx->qkeys2.as<uint32_t>(), idx->qperm.as<uint32_t>(), idx->qperm2.as<uint32_t>(), (int)nq, 0, bits, s));
         g_launches += 4;

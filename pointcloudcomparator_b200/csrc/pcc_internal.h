@@ -70,6 +70,9 @@ struct pcc_index {
     uint64_t grid_gen = 0;     // bumped by pcc_build / pcc_adopt
     void *comm = nullptr;      // ncclComm_t handed to pcc_comm_init (not owned); rank / world of this process in it
     int comm_rank = 0, comm_world = 1;
+    // host-side launch cost matters once a rank's shard is ~1 M queries (0.5 ms of GPU work per call): CUB's temp-size queries and
+    // the per-function attributes are done once, not per call
+    int64_t sel_tmp_nq = -1; size_t sel_tmp_bytes = 0; int64_t sort_tmp_nq = -1; int sort_tmp_bits = 0; size_t sort_tmp_bytes = 0;
     bool icp_allreduce = false;   // pcc_icp_step sums its 17 doubles over the ranks (set by pcc_icp_align while it runs on a sharded source)
     int calib_k = -1;          // k the logging-threshold table in `calib` was calibrated for (-1: none), on grid generation calib_gen of the grid owner
     uint64_t calib_gen = 0;

@@ -895,16 +895,19 @@ static int calibrate_thr(pcc_index *idx, const Grid &g, const QueryView &v, int 
 }
 template <int K>
 static int launch_knn_fast(pcc_index *idx, const Grid &g, const QueryView &v, int k, int32_t *oi, float *od, int vec4, FixList fix, cudaStream_t s) {
-    size_t tmp = 0;
-    cub::DeviceSelect::Flagged(nullptr, tmp, cub::CountingInputIterator<uint32_t>(0), fix.ring_flag, fix.ring_list, fix.ring_count, (int)v.nq, s);
+    size_t tmp = idx->sel_tmp_bytes;
+    if (idx->sel_tmp_nq != v.nq) {
+        cub::DeviceSelect::Flagged(nullptr, tmp, cub::CountingInputIterator<uint32_t>(0), fix.ring_flag, fix.ring_list, fix.ring_count, (int)v.nq, s);
+        idx->sel_tmp_nq = v.nq; idx->sel_tmp_bytes = tmp;
+    }
     PCC_TRY(idx->cub_tmp.reserve(tmp));
     if (!idx->aux_stream) {
         PCC_CUDA(cudaStreamCreateWithFlags(&idx->aux_stream, cudaStreamNonBlocking));
         PCC_CUDA(cudaEventCreateWithFlags(&idx->ev_fork, cudaEventDisableTiming));
         PCC_CUDA(cudaEventCreateWithFlags(&idx->ev_join, cudaEventDisableTiming));
     }
-    cudaMemsetAsync(fix.count, 0, sizeof(unsigned), s);
-    cudaMemsetAsync(fix.wide_count, 0, 3 * sizeof(unsigned), s);          // wide_count, late_count and retry_count are adjacent
+    if (fix.stats) { cudaMemsetAsync(fix.count, 0, sizeof(unsigned), s); cudaMemsetAsync(fix.wide_count, 0, 3 * sizeof(unsigned), s); }      // the stats words sit between the counters
+    else cudaMemsetAsync(fix.count, 0, 33 * sizeof(unsigned), s);           // count [0] ... wide_count, late_count, retry_count [30..32] in one go
     static const bool old_fast_env = getenv("PCC_OLD_FAST") != nullptr;   // measurement aid: the round-1 block kernel (sorted insertion + candidate log)
     // Measured on B200, 10 M queries vs the 10 M-point surface cloud (profiles/r2/sweep_k_blockkernel.txt): the threshold kernel wins at
     // K = 16 (3.50 vs 3.81 ms), ties at K = 8 (2.53 / 2.51) and loses at K = 4 (2.28 / 2.07: ~10 logged candidates do not pay for a
@@ -926,10 +929,14 @@ static int launch_knn_fast(pcc_index *idx, const Grid &g, const QueryView &v, in
             idx->calib_k = k; idx->calib_gen = owner->grid_gen;
         }
         const float *ratio = (const float *)(idx->calib.as<unsigned>() + kCalibBuckets * kCalibBins);
-        PCC_CUDA(cudaFuncSetAttribute(knn_thr_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThrCfg<K>::smem));
-        PCC_CUDA(cudaFuncSetAttribute(knn_thr_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThrCfg<K>::smem));
-        PCC_CUDA(cudaFuncSetAttribute(knn_thr_retry_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThrCfg<K>::smem));
-        PCC_CUDA(cudaFuncSetAttribute(knn_thr_retry_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThrCfg<K>::smem));
+        static std::atomic<unsigned long long> attr_done{0};            // per device, once per process (5-10 us each otherwise, every call)
+        if (!((attr_done.load() >> (idx->device & 63)) & 1ull)) {
+            PCC_CUDA(cudaFuncSetAttribute(knn_thr_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThrCfg<K>::smem));
+            PCC_CUDA(cudaFuncSetAttribute(knn_thr_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThrCfg<K>::smem));
+            PCC_CUDA(cudaFuncSetAttribute(knn_thr_retry_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThrCfg<K>::smem));
+            PCC_CUDA(cudaFuncSetAttribute(knn_thr_retry_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThrCfg<K>::smem));
+            attr_done.fetch_or(1ull << (idx->device & 63));
+        }
         if (k == K) {
             knn_thr_kernel<K, true><<<nblocks(v.nq, ThrCfg<K>::threads), ThrCfg<K>::threads, ThrCfg<K>::smem, s>>>(g, v, k, oi, od, vec4, fix, ratio);
             PCC_LAUNCHED();
@@ -947,7 +954,7 @@ static int launch_knn_fast(pcc_index *idx, const Grid &g, const QueryView &v, in
     // fork: the wide queries (and a short tied list) on the aux stream, beside the compaction + ring pass on `s`
     PCC_CUDA(cudaEventRecord(idx->ev_fork, s));
     PCC_CUDA(cudaStreamWaitEvent(idx->aux_stream, idx->ev_fork, 0));
-    knn_wide_kernel<<<148 * 6, 128, 0, idx->aux_stream>>>(g, v, k, oi, od, fix, fix.wide_list, fix.wide_count, 1);
+    knn_wide_kernel<<<148 * 6, 128, 0, idx->aux_stream>>>(g, v, k, oi, od, fix, fix.wide_list, fix.wide_count, old_fast ? 1 : 0);
     PCC_LAUNCHED();
     PCC_CUDA(cudaEventRecord(idx->ev_join, idx->aux_stream));
     PCC_CUDA(cub::DeviceSelect::Flagged(idx->cub_tmp.p, tmp, cub::CountingInputIterator<uint32_t>(0), fix.ring_flag, fix.ring_list, fix.ring_count, (int)v.nq, s));
@@ -957,8 +964,10 @@ static int launch_knn_fast(pcc_index *idx, const Grid &g, const QueryView &v, in
     PCC_CUDA(cudaStreamWaitEvent(s, idx->ev_join, 0));
     knn_wide_kernel<<<148 * 2, 128, 0, s>>>(g, v, k, oi, od, fix, fix.late_list, fix.late_count, 0);      // what the ring pass handed on (rare)
     PCC_LAUNCHED();
-    knn_fixup_kernel<K><<<148 * 4, 128, 0, s>>>(g, v, k, oi, od, vec4, fix);
-    PCC_LAUNCHED();
+    if (old_fast) {                  // the threshold kernel settles its ties in knn_thr_retry_kernel: nothing is listed for the fix-up kernel
+        knn_fixup_kernel<K><<<148 * 4, 128, 0, s>>>(g, v, k, oi, od, vec4, fix);
+        PCC_LAUNCHED();
+    }
     return PCC_OK;
 }
 
