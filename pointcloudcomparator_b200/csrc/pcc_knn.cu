@@ -937,7 +937,19 @@ static int launch_knn_fast(pcc_index *idx, const Grid &g, const QueryView &v, in
             PCC_CUDA(cudaFuncSetAttribute(knn_thr_retry_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThrCfg<K>::smem));
             attr_done.fetch_or(1ull << (idx->device & 63));
         }
-        if (k == K) {
+        const char *staged_env = getenv("PCC_THR_STAGED");              // TMA-staged variant: opt-in, read per call so a test can switch it (measured slower)
+        const bool staged = staged_env && atoi(staged_env) != 0;
+        if (staged && k == K) {
+            static std::atomic<unsigned long long> sattr_done{0};
+            if (!((sattr_done.load() >> (idx->device & 63)) & 1ull)) {
+                PCC_CUDA(cudaFuncSetAttribute(knn_thr_staged_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ThrStagedCfg<K>::smem));
+                sattr_done.fetch_or(1ull << (idx->device & 63));
+            }
+            knn_thr_staged_kernel<K, true><<<nblocks(v.nq, ThrCfg<K>::threads), ThrCfg<K>::threads, ThrStagedCfg<K>::smem, s>>>(g, v, k, oi, od, vec4, fix, ratio);
+            PCC_LAUNCHED();
+            knn_thr_retry_kernel<K, true><<<148 * 4, ThrCfg<K>::threads, ThrCfg<K>::smem, s>>>(g, v, k, oi, od, vec4, fix, ratio);
+            PCC_LAUNCHED();
+        } else if (k == K) {
             knn_thr_kernel<K, true><<<nblocks(v.nq, ThrCfg<K>::threads), ThrCfg<K>::threads, ThrCfg<K>::smem, s>>>(g, v, k, oi, od, vec4, fix, ratio);
             PCC_LAUNCHED();
             knn_thr_retry_kernel<K, true><<<148 * 4, ThrCfg<K>::threads, ThrCfg<K>::smem, s>>>(g, v, k, oi, od, vec4, fix, ratio);

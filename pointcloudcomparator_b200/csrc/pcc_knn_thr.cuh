@@ -198,7 +198,9 @@ __device__ __forceinline__ void prefetch_run(const float4 *pts, uint32_t j, uint
 #define PCC_THR_PIPE 0
 #endif
 struct Quad { float4 p0, p1, p2, p3; };
-__device__ __forceinline__ Quad load_quad(const float4 *__restrict__ pts, uint32_t j) { Quad q; q.p0 = __ldg(pts + j); q.p1 = __ldg(pts + j + 1); q.p2 = __ldg(pts + j + 2); q.p3 = __ldg(pts + j + 3); return q; }
+// GEN: `pts` may point into the warp's shared-memory tile (staged kernel) -- plain generic loads; otherwise read-only global loads
+template <bool GEN> __device__ __forceinline__ float4 load_pt(const float4 *pts, uint32_t j) { if (GEN) return pts[j]; return __ldg(pts + j); }
+template <bool GEN> __device__ __forceinline__ Quad load_quad(const float4 *pts, uint32_t j) { Quad q; q.p0 = load_pt<GEN>(pts, j); q.p1 = load_pt<GEN>(pts, j + 1); q.p2 = load_pt<GEN>(pts, j + 2); q.p3 = load_pt<GEN>(pts, j + 3); return q; }
 template <uint32_t STRIDE, bool COMPRESS, class F>
 __device__ __forceinline__ void thr_quad(const Quad &q, const uint32_t j, const float x, const float y, const float z, float &T, float &dmin, float &tau, uint32_t &wa, const uint32_t cap, F &&on_full) {
     const float d0 = dist2(x, y, z, q.p0.x, q.p0.y, q.p0.z), d1 = dist2(x, y, z, q.p1.x, q.p1.y, q.p1.z), d2 = dist2(x, y, z, q.p2.x, q.p2.y, q.p2.z), d3 = dist2(x, y, z, q.p3.x, q.p3.y, q.p3.z);
@@ -213,21 +215,21 @@ __device__ __forceinline__ void thr_quad(const Quad &q, const uint32_t j, const 
 // PCC_THR_PIPE = 1 software-pipelines the walk (the four loads of step i+1 are issued before step i is processed, two register
 // sets, loop unrolled by two).  Measured on B200: no gain (3.62 vs 3.51 ms for the stage, and the retry kernel doubles) -- the
 // exposed time is not the latency of one step's loads (profiles/r2/blockkernel_load_experiments.txt), so it is off by default.
-template <uint32_t STRIDE, bool COMPRESS, class F>
-__device__ __forceinline__ void thr_walk_run(const Grid &g, uint32_t j, const uint32_t e, const float x, const float y, const float z, float &T,
+template <uint32_t STRIDE, bool COMPRESS, bool GEN, class F>
+__device__ __forceinline__ void thr_walk_run(const float4 *pts, uint32_t j, const uint32_t e, const float x, const float y, const float z, float &T,
                                              float &dmin, float &tau, uint32_t &wa, const uint32_t cap, F &&on_full) {
 #if PCC_THR_PIPE
     bool have_a = j + 4 <= e;
     Quad a, b;
-    if (have_a) a = load_quad(g.pts, j);
+    if (have_a) a = load_quad<GEN>(pts, j);
     while (have_a) {
         const bool have_b = j + 8 <= e;
-        if (have_b) b = load_quad(g.pts, j + 4);
+        if (have_b) b = load_quad<GEN>(pts, j + 4);
         thr_quad<STRIDE, COMPRESS>(a, j, x, y, z, T, dmin, tau, wa, cap, on_full);
         j += 4;
         if (!have_b) break;
         have_a = j + 8 <= e;
-        if (have_a) a = load_quad(g.pts, j + 4);
+        if (have_a) a = load_quad<GEN>(pts, j + 4);
         thr_quad<STRIDE, COMPRESS>(b, j, x, y, z, T, dmin, tau, wa, cap, on_full);
         j += 4;
     }
@@ -239,12 +241,12 @@ __device__ __forceinline__ void thr_walk_run(const Grid &g, uint32_t j, const ui
     // lane: L1 hits, same wavefront count); 2 = every lane reads point 0 (one wavefront per load: pure issue cost)
     const uint32_t j0 = j;
     for (; j + 4 <= e; j += 4) {
-        const Quad a = load_quad(g.pts, PCC_THR_EXP == 1 ? j0 : (PCC_THR_EXP == 2 ? 0u : j));
+        const Quad a = load_quad<GEN>(pts, PCC_THR_EXP == 1 ? j0 : (PCC_THR_EXP == 2 ? 0u : j));
         thr_quad<STRIDE, COMPRESS>(a, j, x, y, z, T, dmin, tau, wa, cap, on_full);
     }
 #endif
     if (j < e) {                                          // 1..3 left: the loads are clamped to the run, the extra lanes never advance
-        const float4 p0 = __ldg(g.pts + j), p1 = __ldg(g.pts + min(j + 1, e - 1)), p2 = __ldg(g.pts + min(j + 2, e - 1));
+        const float4 p0 = load_pt<GEN>(pts, j), p1 = load_pt<GEN>(pts, min(j + 1, e - 1)), p2 = load_pt<GEN>(pts, min(j + 2, e - 1));
         const float d0 = dist2(x, y, z, p0.x, p0.y, p0.z), d1 = dist2(x, y, z, p1.x, p1.y, p1.z), d2 = dist2(x, y, z, p2.x, p2.y, p2.z);
         sts_v2(wa, __float_as_uint(d0), j); advance_if_le<STRIDE>(wa, d0, tau);
         sts_v2(wa, __float_as_uint(d1), j + 1); advance_if_le_and<STRIDE>(wa, d1, tau, j + 1 < e);
@@ -265,26 +267,55 @@ __device__ __forceinline__ void thr_walk_run(const Grid &g, uint32_t j, const ui
 //   * a tie the 32-bit keys cannot order: the k smallest are picked from the log with exact 64-bit (d2, index) keys.
 // Only what is still unsettled after that (more ties than the log holds) runs the exact per-thread search with ring expansion.
 constexpr float kRetryScale = 4.f;
-template <int K, bool FULLK, bool RETRY>
+// STAGED (knn_thr_staged_kernel): the candidate points are not loaded lane by lane from global memory.  The lanes of a warp that share
+// the (y, z) row of its first live query -- queries are in cell order, so that is nearly all of them -- span a few adjacent cells; the
+// union of their nine stencil rows is nine contiguous runs of the sorted array (~250 points), which lanes 0..8 pull into the warp's
+// shared-memory tile with cp.async.bulk (TMA bulk copy, completion on an mbarrier).  Every lane then walks its own window of the
+// tile; lanes outside the leader's row, or a union that does not fit the tile, keep the global path.  Why: the per-lane loads are
+// what the measurements leave as removable cost (0.8 of 2.5 ms in misses, ~8 L1 sector wavefronts per load).
+#ifndef PCC_THR_TILE
+#define PCC_THR_TILE 384
+#endif
+namespace thr_tma {
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+}  // namespace thr_tma
+template <int K, bool FULLK, bool RETRY, bool STAGED = false>
 __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, const int64_t t, const int k_rt, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4,
-                                             const FixList &fix, const float *__restrict__ ratio, uint2 *__restrict__ slog, const bool loose = false) {
+                                             const FixList &fix, const float *__restrict__ ratio, uint2 *__restrict__ slog, const bool loose = false,
+                                             float4 *tile = nullptr, unsigned long long *bar = nullptr) {
     constexpr int TH = ThrCfg<K>::threads, SLOTS = ThrCfg<K>::slots, B = ThrCfg<K>::B;
     constexpr uint32_t SMASK = (1u << ThrCfg<K>::slot_bits) - 1u;
     const int k = FULLK ? K : k_rt;
-    float x, y, z; int64_t row; bool empty;
+    float x = 0.f, y = 0.f, z = 0.f; int64_t row = 0; bool empty = false;
     const bool live = load_query(g, v, t, x, y, z, row, empty);
-    if (!live) {
+    auto leave_dead = [&]() {                             // tail thread or non-finite query
         if (t < v.nq) fix.ring_flag[t] = 0;
         if (empty) { nkey_t e[K];
 #pragma unroll
             for (int j = 0; j < K; ++j) e[j] = PCC_EMPTY_KEY;
             write_row<K>(e, k, out_idx + row * k, out_d2 + row * k, vec4); }
-        return;
-    }
-    const QueryCell c = locate(g, x, y, z);
+    };
+    if (!STAGED && !live) { leave_dead(); return; }       // the staged kernel keeps every lane until the tile is in (warp-wide shuffles)
+    QueryCell c; c.cx = c.cy = c.cz = 0; c.ux = c.uy = c.uz = 0.f;
+    if (live) c = locate(g, x, y, z);
     // the 9 run bounds of the block: its population M, and a first bound for dmin (the middle point of the query's own row)
     uint32_t M = 0, s0 = 0, e0 = 0;
-    {
+    if (live) {
         const int xa = max(c.cx - 1, 0), xb = min(c.cx + 1, g.nx - 1);
         uint32_t rs[9], re[9];
 #pragma unroll
@@ -297,18 +328,55 @@ __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, 
             }
         }
 #pragma unroll
-        for (int r = 0; r < 9; ++r) { M += re[r] - rs[r]; if (PCC_THR_PREFETCH & 1) prefetch_run<3, false>(g.pts, rs[r], re[r]); }
+        for (int r = 0; r < 9; ++r) { M += re[r] - rs[r]; if (!STAGED && (PCC_THR_PREFETCH & 1)) prefetch_run<3, false>(g.pts, rs[r], re[r]); }
         s0 = rs[0]; e0 = re[0];
     }
-    if (M < (uint32_t)k) {                                // fewer than k points in the block: a wide query (no walk)
+    auto leave_wide = [&]() {                             // fewer than k points in the block: a wide query (no walk)
         fix.ring_flag[t] = 0;
         if (fix.stats) { atomicAdd(fix.stats + 0, 1ull); atomicAdd(fix.stats + 4, 1ull); }
         push_list(fix.wide_list, fix.wide_count, (uint32_t)t);
-        return;
+    };
+    const bool walker = live && M >= (uint32_t)k;
+    if (!STAGED && !walker) { leave_wide(); return; }
+    // ---- staged kernel: pull the union of the leader row's nine runs into the warp's tile ----
+    bool lane_staged = false;
+    uint32_t my_start = 0, my_off = 0;                    // lane r < 9: first sorted position / tile offset of stencil row r of the union
+    if (STAGED) {
+        const unsigned full = 0xffffffffu;
+        const int lane = threadIdx.x & 31;
+        const unsigned wmask = __ballot_sync(full, walker);
+        if (wmask) {
+            const int leader = __ffs(wmask) - 1;
+            const int lcy = __shfl_sync(full, c.cy, leader), lcz = __shfl_sync(full, c.cz, leader);
+            bool inrow = walker && c.cy == lcy && c.cz == lcz;
+            const int xmin = __reduce_min_sync(full, inrow ? c.cx : 0x7fffffff);
+            inrow = inrow && c.cx <= xmin + 9;            // at most 12 cells per staged row
+            const int xmax = __reduce_max_sync(full, inrow ? c.cx : xmin);
+            uint32_t len = 0;
+            if (lane < 9) {
+                const int zz = lcz + centre_out(lane / 3), yy = lcy + centre_out(lane % 3);
+                if (zz >= 0 && zz < g.nz && yy >= 0 && yy < g.ny) {
+                    const uint32_t *rowp = g.cell_start + ((size_t)zz * g.ny + yy) * g.nx;
+                    my_start = __ldg(rowp + max(xmin - 1, 0)); len = __ldg(rowp + min(xmax + 1, g.nx - 1) + 1) - my_start;
+                }
+            }
+            uint32_t inc = len;
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) { const uint32_t w = __shfl_up_sync(full, inc, o); if (lane >= o) inc += w; }
+            my_off = inc - len;
+            const uint32_t total = __shfl_sync(full, inc, 8);
+            if (total <= (uint32_t)PCC_THR_TILE && total > 0) {
+                if (lane == 0) thr_tma::mbar_expect_tx(bar, total * 16u);
+                __syncwarp();
+                if (lane < 9 && len) thr_tma::bulk_g2s(tile + my_off, g.pts + my_start, len * 16u, bar);
+                lane_staged = inrow;
+                thr_tma::mbar_wait(bar, 0);
+            }
+        }
     }
-    float T = __ldg(ratio + min(M >> 2, (uint32_t)kCalibBuckets - 1u)) * (float)k / (float)M * (g.cell * g.cell) * ((RETRY && loose) ? kRetryScale : 1.f);
+    float T = __ldg(ratio + min(M >> 2, (uint32_t)kCalibBuckets - 1u)) * (float)k / (float)max(M, 1u) * (g.cell * g.cell) * ((RETRY && loose) ? kRetryScale : 1.f);
     float dmin = CUDART_INF_F;
-    if (e0 > s0) { const float4 p = __ldg(g.pts + ((s0 + e0) >> 1)); dmin = dist2(x, y, z, p.x, p.y, p.z); }
+    if (walker && e0 > s0) { const float4 p = __ldg(g.pts + ((s0 + e0) >> 1)); dmin = dist2(x, y, z, p.x, p.y, p.z); }
     float tau = dmin + T;
     constexpr uint32_t STRIDE = (uint32_t)TH * (uint32_t)sizeof(uint2);
     constexpr int LOGCAP = SLOTS - 4;
@@ -356,17 +424,28 @@ __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, 
     };
     // the walk: rows centre-out, each clipped to the ball of the current tau (bounds of row i+1 fetched before row i is walked)
     {
+        const RowRuns none = {0u, 0u, 0u, 0u};
         int az = 0, ay = 0;
-        RowRuns nxt = row_runs(g, c, -1, 1, to_cell_units(g, tau), 0, 0);
+        RowRuns nxt = walker ? row_runs(g, c, -1, 1, to_cell_units(g, tau), 0, 0) : none;
         for (;;) {
             const RowRuns cur = nxt;
+            const int r = az * 3 + ay;
             if (++ay == 3) { ay = 0; ++az; }
             const bool more = az < 3;
-            if (more) { nxt = row_runs(g, c, -1, 1, to_cell_units(g, tau), az, ay); if (PCC_THR_PREFETCH & 2) prefetch_run<3, true>(g.pts, nxt.j1, nxt.e1); }
-            thr_walk_run<STRIDE, RETRY>(g, cur.j1, cur.e1, x, y, z, T, dmin, tau, wa, cap, on_full);
+            if (more && walker) { nxt = row_runs(g, c, -1, 1, to_cell_units(g, tau), az, ay); if (!STAGED && (PCC_THR_PREFETCH & 2)) prefetch_run<3, true>(g.pts, nxt.j1, nxt.e1); }
+            if (STAGED) {
+                // sorted position j of stencil row r sits at tile[off_r + (j - start_r)]: a lane in the leader's row reads the tile
+                // (its own cell lies inside the staged x-range, so its window does too), any other lane reads global memory
+                const uint32_t st = __shfl_sync(0xffffffffu, my_start, r), of = __shfl_sync(0xffffffffu, my_off, r);
+                const float4 *src = lane_staged ? (const float4 *)tile + of - st : g.pts;
+                thr_walk_run<STRIDE, RETRY, true>(src, cur.j1, cur.e1, x, y, z, T, dmin, tau, wa, cap, on_full);
+            } else thr_walk_run<STRIDE, RETRY, false>(g.pts, cur.j1, cur.e1, x, y, z, T, dmin, tau, wa, cap, on_full);
+            (void)r;
             if (!more) break;
         }
     }
+    if (STAGED && !live) { leave_dead(); return; }
+    if (STAGED && !walker) { leave_wide(); return; }
     if (RETRY && give_up) { fix.ring_flag[t] = 0; knn_reg_body<K>(g, v, t, k, out_idx, out_d2, vec4); return; }
     const int n = (int)((wa - wa0) / STRIDE);             // == LOGCAP: the log (may have) overflowed
     select_log(n);
@@ -432,6 +511,26 @@ template <int K, bool FULLK>
 __global__ void __launch_bounds__(ThrCfg<K>::threads, ThrCfg<K>::min_blocks) knn_thr_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4, FixList fix, const float *__restrict__ ratio) {
     extern __shared__ uint2 thr_log[];
     knn_thr_body<K, FULLK, false>(g, v, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, k, out_idx, out_d2, vec4, fix, ratio, thr_log + threadIdx.x);
+}
+#ifndef PCC_THR_STAGED_MB
+#define PCC_THR_STAGED_MB 3
+#endif
+template <int K> struct ThrStagedCfg {
+    static constexpr int warps = ThrCfg<K>::threads / 32;
+    static constexpr size_t log_bytes = ThrCfg<K>::smem, tile_bytes = (size_t)warps * PCC_THR_TILE * sizeof(float4);
+    static constexpr size_t smem = log_bytes + tile_bytes + warps * sizeof(unsigned long long);
+};
+template <int K, bool FULLK>
+__global__ void __launch_bounds__(ThrCfg<K>::threads, PCC_THR_STAGED_MB) knn_thr_staged_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4, FixList fix, const float *__restrict__ ratio) {
+    extern __shared__ __align__(128) unsigned char thr_smem[];
+    uint2 *log = reinterpret_cast<uint2 *>(thr_smem);
+    float4 *tiles = reinterpret_cast<float4 *>(thr_smem + ThrStagedCfg<K>::log_bytes);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(thr_smem + ThrStagedCfg<K>::log_bytes + ThrStagedCfg<K>::tile_bytes);
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) thr_tma::mbar_init(bars + warp, 1);
+    __syncwarp();
+    knn_thr_body<K, FULLK, false, true>(g, v, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, k, out_idx, out_d2, vec4, fix, ratio, log + threadIdx.x, false,
+                                        tiles + (size_t)warp * PCC_THR_TILE, bars + warp);
 }
 template <int K, bool FULLK>
 __global__ void __launch_bounds__(ThrCfg<K>::threads, 2) knn_thr_retry_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4, FixList fix, const float *__restrict__ ratio) {

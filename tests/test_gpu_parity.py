@@ -476,6 +476,32 @@ def test_query_batch_size_guard(GS):
     assert rc == -1 and b"nq" in L.pcc_last_error()
 
 
+def test_tma_staged_block_kernel_parity(GS, monkeypatch):
+    """knn_thr_staged_kernel (PCC_THR_STAGED=1): the warp's union stencil pulled into shared memory with cp.async.bulk + mbarrier, lanes walk
+    their windows of the tile.  Opt-in (measured slower than the per-lane walk), but exact: same rows as the oracle on a surface cloud with
+    external noisy queries (mixed warps: lanes outside the leader's row keep the global path), on self-queries, and on a clustered cloud
+    whose dense unions do not fit the tile."""
+    monkeypatch.setenv("PCC_THR_STAGED", "1")
+    ref = synth.room(120000, 1001)
+    qry = synth.sweep_queries(ref, 50000, seed=11, sigma=0.01)
+    tree = oracle.KdTree(ref)
+    s = GS().setInputCloud(ref, k_hint=16)
+    for k in (16, 12):                                      # 12: K = 16 template with k < K takes the non-staged kernel
+        gi, gd, _ = s.nearestKSearch(qry, k)
+        oi, od, _ = tree.knn(qry, k)
+        assert_knn_equal(gi, gd, oi, od)
+    gi, gd, _ = s.nearestKSearch(None, 16)
+    oi, od, _ = tree.knn(ref, 16)
+    assert_knn_equal(gi, gd, oi, od)
+    rng = np.random.default_rng(5)
+    c = rng.normal(0, 1.0, (6, 3))
+    dense = (c[rng.integers(0, 6, 60000)] + rng.normal(0, 0.01, (60000, 3)) * rng.choice([1.0, 10.0], (60000, 1))).astype(np.float32)
+    q2 = (dense[::3] + rng.normal(0, 0.002, (20000, 3))).astype(np.float32)
+    gi, gd, _ = GS().setInputCloud(dense, k_hint=16).nearestKSearch(q2, 16)
+    oi, od, _ = oracle.KdTree(dense).knn(q2, 16)
+    assert_knn_equal(gi, gd, oi, od)
+
+
 def test_voxel_grid_leaf_too_small_passes_input_through(GS):
     """PCL 1.7 VoxelGrid::applyFilter warns and returns the input unfiltered when the voxel index would overflow int32
     (src/segmentation.cpp:69-74 would then cluster the full cloud); product and oracle both mirror that instead of failing."""
