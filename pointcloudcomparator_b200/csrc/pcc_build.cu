@@ -202,13 +202,17 @@ int prepare_queries(pcc_index *idx, const void *q, int64_t nq, int stride_bytes,
     out->order = nullptr;
     if (sort) {
         int bits = 1; while ((1ll << bits) <= idx->gh.n_cells && bits < 32) ++bits;
+        // The order only serves locality, so the lowest key bits (runs of 2^low adjacent x-cells) may stay unsorted: PCC_SORT_LOW_BITS
+        // (measurement knob, default 0 = full order; 26-bit keys take four 8-bit radix passes, 24 bits three).
+        static const int low_env = getenv("PCC_SORT_LOW_BITS") ? atoi(getenv("PCC_SORT_LOW_BITS")) : 0;
+        const int low = std::max(0, std::min(low_env, bits - 8));
         size_t tmp = idx->sort_tmp_bytes;
         if (idx->sort_tmp_nq != nq || idx->sort_tmp_bits != bits) {
-            cub::DeviceRadixSort::SortPairs(nullptr, tmp, idx->qkeys.as<uint32_t>(), idx->qkeys2.as<uint32_t>(), idx->qperm.as<uint32_t>(), idx->qperm2.as<uint32_t>(), (int)nq, 0, bits, s);
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp, idx->qkeys.as<uint32_t>(), idx->qkeys2.as<uint32_t>(), idx->qperm.as<uint32_t>(), idx->qperm2.as<uint32_t>(), (int)nq, low, bits, s);
             idx->sort_tmp_nq = nq; idx->sort_tmp_bits = bits; idx->sort_tmp_bytes = tmp;
         }
         PCC_TRY(idx->cub_tmp.reserve(tmp));
-        PCC_CUDA(cub::DeviceRadixSort::SortPairs(idx->cub_tmp.p, tmp, idx->qkeys.as<uint32_t>(), idx->qkeys2.as<uint32_t>(), idx->qperm.as<uint32_t>(), idx->qperm2.as<uint32_t>(), (int)nq, 0, bits, s));
+        PCC_CUDA(cub::DeviceRadixSort::SortPairs(idx->cub_tmp.p, tmp, idx->qkeys.as<uint32_t>(), idx->qkeys2.as<uint32_t>(), idx->qperm.as<uint32_t>(), idx->qperm2.as<uint32_t>(), (int)nq, low, bits, s));
         g_launches += 4;
         out->order = idx->qperm2.as<uint32_t>();
     }

@@ -1086,7 +1086,7 @@ int pcc_knn(pcc_index *idx, const void *q, int64_t nq, int stride_bytes, int k, 
     cudaStream_t s = (cudaStream_t)stream;
     // Large host batches: two-slot pipeline, 1 Mi queries per chunk (16 MB in, k x 8 MB out), so the device->host copy of
     // chunk i overlaps the search of chunk i+1 and the host->device copy of chunk i+2 (PCIe is full duplex).
-    static constexpr int64_t kChunk = 1 << 20;
+    static const int64_t kChunk = getenv("PCC_PIPE_CHUNK_LOG2") ? (1ll << std::max(16, std::min(24, atoi(getenv("PCC_PIPE_CHUNK_LOG2"))))) : (1ll << 20);      // measured on B200 (profiles/r2/e2e_chunk_probe.txt): 2^20 wins
     if (mem == PCC_HOST && q && nq >= 2 * kChunk && !idx->timing && stride_bytes >= 12 && !(stride_bytes & 3)) {
         if (!out_idx || !out_d2) return fail(PCC_ERR_INVALID, "output pointers are NULL");
         if (!idx->shadow) {
