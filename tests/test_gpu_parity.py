@@ -502,6 +502,31 @@ def test_tma_staged_block_kernel_parity(GS, monkeypatch):
     assert_knn_equal(gi, gd, oi, od)
 
 
+@pytest.mark.parametrize("k", [9, 13, 15, 16])
+def test_threshold_block_kernel_paths(GS, k):
+    """knn_thr_kernel<16> serves 8 < k <= 16 on batches >= 1024: k < 16 takes its runtime-k instantiation; a reference cloud smaller than k
+    sends every query to the wide pass; far-away and clamped queries, exact duplicates (ties -> 64-bit selection from the log in the retry
+    pass) and a very dense clump (log overflow -> in-place compression in the retry pass) all have to come out bit-exact."""
+    rng = np.random.default_rng(40 + k)
+    ref = synth.room(80000, 1001, size=(3.0, 2.0, 1.5))
+    dup = ref[rng.integers(0, len(ref), 3000)]                                         # exact duplicates: d2 ties at every rank
+    clump = (ref[123] + rng.normal(0, 2e-4, (4000, 3))).astype(np.float32)             # 4000 points inside one cell
+    ref2 = np.concatenate([ref, dup, clump]).astype(np.float32)
+    ref2 = ref2[rng.permutation(len(ref2))]
+    qry = np.concatenate([synth.sweep_queries(ref2, 6000, seed=k, sigma=0.01), dup[:500], clump[:500] + np.float32(1e-4),
+                          rng.uniform(-5, 8, (300, 3)).astype(np.float32), np.array([[1e3, -1e3, 5e2], [np.nan, 0, 0]], np.float32)]).astype(np.float32)
+    tree = oracle.KdTree(ref2)
+    gi, gd, keff = GS().setInputCloud(ref2, k_hint=k).nearestKSearch(qry, k)
+    oi, od, _ = tree.knn(qry, k)
+    assert keff == k
+    assert_knn_equal(gi, gd, oi, od)
+    tiny = ref[:k - 3]                                                                  # fewer points than k: (-1, +inf) padding, every query "wide"
+    gi, gd, keff = GS().setInputCloud(tiny, k_hint=k).nearestKSearch(qry[:2000], k)
+    oi, od, okeff = oracle.KdTree(tiny).knn(qry[:2000], k)
+    assert keff == okeff == k - 3
+    assert_knn_equal(gi, gd, oi, od)
+
+
 def test_voxel_grid_leaf_too_small_passes_input_through(GS):
     """PCL 1.7 VoxelGrid::applyFilter warns and returns the input unfiltered when the voxel index would overflow int32
     (src/segmentation.cpp:69-74 would then cluster the full cloud); product and oracle both mirror that instead of failing."""
