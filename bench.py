@@ -39,7 +39,7 @@ def workload_config(args, world):
         "workload": f"raw kNN sweep point (BASELINE configs[4], the split of configs[3]): k={args.k}, ONE set of Q={args.nq} queries vs N={args.n} reference points, "
                     f"{args.cloud} cloud (S5/S4 generators, seeds 4001/5002), queries = reference points + N(0, 1 cm), shuffled",
         "n_ref": args.n, "n_query_total": args.nq, "n_query_per_gpu": args.nq // max(world, 1), "k": args.k, "cloud": args.cloud,
-        "parallelism": f"query-sharded x{world} by grid-cell range (strong scaling: the same {args.nq} queries at every GPU count), reference grid replicated "
+        "parallelism": f"query-sharded x{world} by grid-cell range (blocks of {args.shard_block} queries of the cell order dealt round-robin; strong scaling: the same {args.nq} queries at every GPU count), reference grid replicated "
                        "(built on rank 0, pcc_broadcast_index = ncclBroadcast); no collective inside the timed region -- the gather of the result table "
                        "(pcc_gather) is timed separately as gather_ms / value_with_gather",
         "l2": "inputs larger than L2 (160 MB grid + 225 MB cell table + 160 MB queries + 1.28 GB output per step, split over the ranks, vs 126 MB L2); no explicit flush",
@@ -237,7 +237,7 @@ def run_ours(args):
 
     # ---- this rank's shard of the common query set (contiguous range of the cell order) ------------
     if world > 1:
-        mine, rows = shard.shard_queries(qry, rank, world, meta[5:8], grid["cell"], grid["dims"])
+        mine, rows = shard.shard_queries(qry, rank, world, meta[5:8], grid["cell"], grid["dims"], block=args.shard_block)
     else:
         mine, rows = qry, None
     nq_local = mine.shape[0]
@@ -261,6 +261,17 @@ def run_ours(args):
 
     ms = _events_ms(step, args.steps, barrier, world, dist, torch)
     launches = launch_count() - l0
+    rank_ms = None
+    if world > 1:                # per-rank time of the same steps (load balance of the shards), gathered for the JSON line
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record(); torch.cuda.synchronize()
+        mine_ms = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
+        allms = [torch.zeros_like(mine_ms) for _ in range(world)]
+        dist.all_gather(allms, mine_ms)
+        rank_ms = [round(float(x.item()), 4) for x in allms]
     value = args.nq * args.steps / (ms * 1e-3)
     _dbg(f"timed steps done {ms:.2f} ms")
 
@@ -412,6 +423,7 @@ def run_ours(args):
             "broadcast_ms": broadcast_ms, "grid": grid,
         }
         if world > 1:
+            line["rank_ms_per_step"] = rank_ms
             line["gather_ms"] = gather_ms
             line["value_with_gather"] = args.nq / ((ms / args.steps + gather_ms) * 1e-3)
             line["gather_bytes_per_rank"] = int(args.nq * args.k * 8)
@@ -459,6 +471,7 @@ def main():
     ap.add_argument("--parity-rows", type=int, default=20000)
     ap.add_argument("--no-c4", action="store_true", help="skip the ICP 10 M vs 10 M arm (BASELINE configs[3])")
     ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling comparison steps at N > 1")
+    ap.add_argument("--shard-block", type=int, default=8192, help="queries per block of the cell order dealt round-robin to the ranks (0 = one contiguous range per rank)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

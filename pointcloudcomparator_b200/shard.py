@@ -41,19 +41,28 @@ def shard_ranges(n: int, world: int):
     return out
 
 
-def shard_queries(queries: np.ndarray, rank: int, world: int, origin=None, cell: float | None = None, dims=None):
+def shard_queries(queries: np.ndarray, rank: int, world: int, origin=None, cell: float | None = None, dims=None, block: int = 0):
     """This rank's share of `queries` and the row numbers it came from.
 
-    With a grid description the queries are first ordered by cell key so each shard is a compact slab of the
+    With a grid description the queries are first ordered by cell key so each shard is made of compact slabs of the
     reference grid (good L2 reuse); without one the split is by input order.
+    block = 0: ONE contiguous range of the cell order per rank.  block > 0: the cell order is cut into blocks of that many
+    queries, dealt to the ranks round-robin -- every rank gets the same number of queries (+-1 block) AND the same mix of
+    easy (flat floor) and hard (edges, clutter) regions; measured on 8 B200s the contiguous split left the slowest rank 40 %
+    behind the fastest although the counts were equal.  Rows stay in cell order inside a shard either way.
     """
     q = np.asarray(queries)
     if origin is not None:
         order = np.argsort(cell_keys(q, origin, cell, dims), kind="stable")
     else:
         order = np.arange(q.shape[0])
-    b, e = shard_ranges(q.shape[0], world)[rank]
-    rows = order[b:e]
+    if block and block > 0 and world > 1:
+        nblk = (q.shape[0] + block - 1) // block
+        mine = [order[b * block:(b + 1) * block] for b in range(rank, nblk, world)]
+        rows = np.concatenate(mine) if mine else order[:0]
+    else:
+        b, e = shard_ranges(q.shape[0], world)[rank]
+        rows = order[b:e]
     return np.ascontiguousarray(q[rows]), rows
 
 
