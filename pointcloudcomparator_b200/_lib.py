@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libpcc_search.so")
+SO_PATH = os.path.abspath(os.environ["PCC_SO"]) if os.environ.get("PCC_SO") else os.path.join(_HERE, "libpcc_search.so")     # PCC_SO: developer builds from scripts/build_variant.sh
 
 HOST, DEVICE = 0, 1
 MAX_K = 512

@@ -294,7 +294,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
                  ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 }  // namespace thr_tma
-template <int K, bool FULLK, bool RETRY, bool STAGED = false>
+#ifndef PCC_THR_MAIN_COMPRESS
+#define PCC_THR_MAIN_COMPRESS 0
+#endif
+// COMPRESS: a full log is compressed in place during the walk (always in the retry pass; in the first pass only in builds with
+// PCC_THR_MAIN_COMPRESS=1, which trade a smaller log -- more resident warps -- for compressions inside the main kernel)
+template <int K, bool FULLK, bool RETRY, bool STAGED = false, bool COMPRESS = RETRY>
 __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, const int64_t t, const int k_rt, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4,
                                              const FixList &fix, const float *__restrict__ ratio, uint2 *__restrict__ slog, const bool loose = false,
                                              float4 *tile = nullptr, unsigned long long *bar = nullptr) {
@@ -438,8 +443,8 @@ __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, 
                 // (its own cell lies inside the staged x-range, so its window does too), any other lane reads global memory
                 const uint32_t st = __shfl_sync(0xffffffffu, my_start, r), of = __shfl_sync(0xffffffffu, my_off, r);
                 const float4 *src = lane_staged ? (const float4 *)tile + of - st : g.pts;
-                thr_walk_run<STRIDE, RETRY, true>(src, cur.j1, cur.e1, x, y, z, T, dmin, tau, wa, cap, on_full);
-            } else thr_walk_run<STRIDE, RETRY, false>(g.pts, cur.j1, cur.e1, x, y, z, T, dmin, tau, wa, cap, on_full);
+                thr_walk_run<STRIDE, COMPRESS, true>(src, cur.j1, cur.e1, x, y, z, T, dmin, tau, wa, cap, on_full);
+            } else thr_walk_run<STRIDE, COMPRESS, false>(g.pts, cur.j1, cur.e1, x, y, z, T, dmin, tau, wa, cap, on_full);
             (void)r;
             if (!more) break;
         }
@@ -447,6 +452,7 @@ __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, 
     if (STAGED && !live) { leave_dead(); return; }
     if (STAGED && !walker) { leave_wide(); return; }
     if (RETRY && give_up) { fix.ring_flag[t] = 0; knn_reg_body<K>(g, v, t, k, out_idx, out_d2, vec4); return; }
+    if (!RETRY && COMPRESS && give_up) { fix.ring_flag[t] = 0; push_list(fix.retry_list, fix.retry_count, (uint32_t)t); return; }      // more ties than slots: the retry pass ends in the exact search
     const int n = (int)((wa - wa0) / STRIDE);             // == LOGCAP: the log (may have) overflowed
     select_log(n);
     // the k-th key, the smallest gap between neighbours among the first k + 1 keys
@@ -510,7 +516,7 @@ __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, 
 template <int K, bool FULLK>
 __global__ void __launch_bounds__(ThrCfg<K>::threads, ThrCfg<K>::min_blocks) knn_thr_kernel(Grid g, QueryView v, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d2, int vec4, FixList fix, const float *__restrict__ ratio) {
     extern __shared__ uint2 thr_log[];
-    knn_thr_body<K, FULLK, false>(g, v, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, k, out_idx, out_d2, vec4, fix, ratio, thr_log + threadIdx.x);
+    knn_thr_body<K, FULLK, false, false, PCC_THR_MAIN_COMPRESS != 0>(g, v, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, k, out_idx, out_d2, vec4, fix, ratio, thr_log + threadIdx.x);
 }
 #ifndef PCC_THR_STAGED_MB
 #define PCC_THR_STAGED_MB 3
