@@ -319,7 +319,7 @@ __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, 
     QueryCell c; c.cx = c.cy = c.cz = 0; c.ux = c.uy = c.uz = 0.f;
     if (live) c = locate(g, x, y, z);
     // the 9 run bounds of the block: its population M, and a first bound for dmin (the middle point of the query's own row)
-    uint32_t M = 0, s0 = 0, e0 = 0;
+    uint32_t M = 0, s0 = 0, e0 = 0, rowmask = 0;         // rowmask bit r: stencil row r holds a point (an empty row costs neither its bounds lookup nor its clipping arithmetic)
     if (live) {
         const int xa = max(c.cx - 1, 0), xb = min(c.cx + 1, g.nx - 1);
         uint32_t rs[9], re[9];
@@ -333,7 +333,7 @@ __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, 
             }
         }
 #pragma unroll
-        for (int r = 0; r < 9; ++r) { M += re[r] - rs[r]; if (!STAGED && (PCC_THR_PREFETCH & 1)) prefetch_run<3, false>(g.pts, rs[r], re[r]); }
+        for (int r = 0; r < 9; ++r) { M += re[r] - rs[r]; rowmask |= (re[r] > rs[r] ? 1u : 0u) << r; if (!STAGED && (PCC_THR_PREFETCH & 1)) prefetch_run<3, false>(g.pts, rs[r], re[r]); }
         s0 = rs[0]; e0 = re[0];
     }
     auto leave_wide = [&]() {                             // fewer than k points in the block: a wide query (no walk)
@@ -431,13 +431,15 @@ __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, 
     {
         const RowRuns none = {0u, 0u, 0u, 0u};
         int az = 0, ay = 0;
-        RowRuns nxt = walker ? row_runs(g, c, -1, 1, to_cell_units(g, tau), 0, 0) : none;
+        if (!walker) rowmask = 0;
+        RowRuns nxt = (rowmask & 1u) ? row_runs(g, c, -1, 1, to_cell_units(g, tau), 0, 0) : none;
         for (;;) {
             const RowRuns cur = nxt;
             const int r = az * 3 + ay;
             if (++ay == 3) { ay = 0; ++az; }
             const bool more = az < 3;
-            if (more && walker) { nxt = row_runs(g, c, -1, 1, to_cell_units(g, tau), az, ay); if (!STAGED && (PCC_THR_PREFETCH & 2)) prefetch_run<3, true>(g.pts, nxt.j1, nxt.e1); }
+            nxt = none;
+            if (more && ((rowmask >> (az * 3 + ay)) & 1u)) { nxt = row_runs(g, c, -1, 1, to_cell_units(g, tau), az, ay); if (!STAGED && (PCC_THR_PREFETCH & 2)) prefetch_run<3, true>(g.pts, nxt.j1, nxt.e1); }
             if (STAGED) {
                 // sorted position j of stencil row r sits at tile[off_r + (j - start_r)]: a lane in the leader's row reads the tile
                 // (its own cell lies inside the staged x-range, so its window does too), any other lane reads global memory
