@@ -104,13 +104,41 @@ __global__ void occupancy_kernel(const uint32_t *__restrict__ cell_start, int64_
         if ((threadIdx.x & 31) == 0) occ[c >> 5] = w;
     }
 }
+struct PopcOp { __device__ __forceinline__ uint32_t operator()(uint32_t w) const { return (uint32_t)__popc(w); } };
+// compact table: occ2[w] = {occ word, non-empty cells before it}; cstart[rank] = cell_start of the rank-th non-empty cell; cstart[total] = n
+__global__ void compact_table_kernel(const uint32_t *__restrict__ occ, const uint32_t *__restrict__ wprefix, int64_t words, const uint32_t *__restrict__ cell_start,
+                                     int64_t n_cells, uint2 *__restrict__ occ2, uint32_t *__restrict__ cstart) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= words) return;
+    uint32_t bits = occ[w], r = wprefix[w];
+    occ2[w] = make_uint2(bits, r);
+    while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; cstart[r++] = cell_start[w * 32 + b]; }
+    if (w == words - 1) cstart[r] = cell_start[n_cells];
+}
 int rebuild_occupancy(pcc_index *idx, cudaStream_t s) {
     const int64_t n_cells = std::max<int64_t>(idx->gh.n_cells, 1);
-    PCC_TRY(idx->occ.reserve((size_t)((n_cells + 31) / 32 + 1) * 4));
-    const int64_t threads = ((n_cells + 31) / 32 + 1) * 32;
+    const int64_t words = (n_cells + 31) / 32 + 1;
+    PCC_TRY(idx->occ.reserve((size_t)words * 4));
+    const int64_t threads = words * 32;
     occupancy_kernel<<<(unsigned)std::min<int64_t>((threads + 255) / 256, 148 * 32), 256, 0, s>>>(idx->cell_start.as<uint32_t>(), idx->gh.n_cells, idx->occ.as<uint32_t>());
     PCC_LAUNCHED();
     PCC_CUDA(cudaGetLastError());
+#if PCC_COMPACT_TABLE      // measurement build: parity-clean, 8 % slower than the dense table on the headline workload
+    PCC_TRY(idx->occ2.reserve((size_t)(words + 1) * sizeof(uint2)));
+    PCC_TRY(idx->cstart.reserve((size_t)(std::min<int64_t>(n_cells, std::max<int64_t>(idx->n_indexed, 0)) + 2) * 4));
+    PCC_TRY(idx->qkeys2.reserve((size_t)words * 4));          // scratch: per-word prefix
+    size_t tmp = 0;
+    cub::TransformInputIterator<uint32_t, PopcOp, const uint32_t *> pc(idx->occ.as<uint32_t>(), PopcOp());
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, pc, idx->qkeys2.as<uint32_t>(), (int)words, s);
+    PCC_TRY(idx->cub_tmp.reserve(tmp));
+    PCC_CUDA(cub::DeviceScan::ExclusiveSum(idx->cub_tmp.p, tmp, pc, idx->qkeys2.as<uint32_t>(), (int)words, s));
+    g_launches += 2;
+    PCC_CUDA(cudaMemsetAsync(idx->occ2.as<uint2>() + words, 0, sizeof(uint2), s));
+    compact_table_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(idx->occ.as<uint32_t>(), idx->qkeys2.as<uint32_t>(), words, idx->cell_start.as<uint32_t>(), idx->gh.n_cells,
+                                                                 idx->occ2.as<uint2>(), idx->cstart.as<uint32_t>());
+    PCC_LAUNCHED();
+    PCC_CUDA(cudaGetLastError());
+#endif
     idx->occ_valid = true;
     return PCC_OK;
 }
@@ -260,7 +288,7 @@ void pcc_destroy(pcc_index *idx) {
     cudaSetDevice(idx->device);
     if (idx->shadow) { pcc_index *sh = idx->shadow; idx->shadow = nullptr; pcc_destroy(sh); }
     for (int i = 0; i < 2; ++i) if (idx->pipe_stream[i]) cudaStreamDestroy(idx->pipe_stream[i]);
-    Buf *bufs[] = {&idx->pts, &idx->cell_start, &idx->occ, &idx->raw, &idx->stage4, &idx->cellrank, &idx->qbuf, &idx->qkeys, &idx->qkeys2, &idx->qperm, &idx->qperm2,
+    Buf *bufs[] = {&idx->pts, &idx->cell_start, &idx->occ, &idx->occ2, &idx->cstart, &idx->raw, &idx->stage4, &idx->cellrank, &idx->qbuf, &idx->qkeys, &idx->qkeys2, &idx->qperm, &idx->qperm2,
                    &idx->cub_tmp, &idx->out_i, &idx->out_f, &idx->out_l, &idx->keys64, &idx->keys64b, &idx->misc, &idx->parent, &idx->inv_pos, &idx->sel_params, &idx->icp_prior, &idx->calib};
     for (Buf *b : bufs) b->release();
     if (idx->h_pinned) cudaFreeHost(idx->h_pinned);

@@ -16,11 +16,28 @@ struct Grid {
     const float4 *pts;            // sorted by cell; .w = original index (int bits)
     const uint32_t *cell_start;   // n_cells + 1
     const uint32_t *occ;          // n_cells bits (+ one padding word): cell holds at least one point
+    const uint2 *occ2;            // per 32 cells: {the occ word, number of non-empty cells before it}
+    const uint32_t *cstart;       // first sorted position of every NON-EMPTY cell, in cell order (+ one entry = n)
     float ox, oy, oz;             // origin = bbox min
     float inv_cell, cell;
     int nx, ny, nz;
     uint32_t n;                   // indexed points
 };
+
+#ifndef PCC_COMPACT_TABLE
+#define PCC_COMPACT_TABLE 0
+#endif
+// first sorted position of cell c (= of the next non-empty cell when c is empty; c = n_cells gives n).  Dense: one load from the
+// n_cells-entry table.  Compact: the rank of c among the non-empty cells from the bitmap word + its prefix, then one load from
+// the table of non-empty cells -- two dependent loads, but 19 MB of tables instead of 225 MB at the headline size.
+__device__ __forceinline__ uint32_t cell_begin(const Grid &g, size_t c) {
+#if PCC_COMPACT_TABLE
+    const uint2 w = __ldg(g.occ2 + (c >> 5));
+    return __ldg(g.cstart + w.y + __popc(w.x & ((1u << (c & 31)) - 1u)));
+#else
+    return __ldg(g.cell_start + c);
+#endif
+}
 
 // Squared L2 exactly as FLANN L2_Simple evaluates it in fp32: ((dx*dx + dy*dy) + dz*dz), no FMA.
 __device__ __forceinline__ float dist2(float qx, float qy, float qz, float px, float py, float pz) {
@@ -135,7 +152,11 @@ struct RowRuns { uint32_t j1, e1, j2, e2; };
 __device__ __forceinline__ bool row_occupied(const Grid &g, size_t base, int xa, int xb) {
     if (xb - xa >= 32) return true;
     const size_t b = base + (size_t)xa;
+#if PCC_COMPACT_TABLE
+    const uint32_t w0 = __ldg(&g.occ2[b >> 5].x), w1 = __ldg(&g.occ2[(b >> 5) + 1].x);
+#else
     const uint32_t w0 = __ldg(g.occ + (b >> 5)), w1 = __ldg(g.occ + (b >> 5) + 1);
+#endif
     const uint32_t bits = __funnelshift_r(w0, w1, (uint32_t)(b & 31));
     const int len = xb - xa + 1;
     return (bits & (len == 32 ? 0xffffffffu : ((1u << len) - 1u))) != 0u;
@@ -156,15 +177,14 @@ __device__ __forceinline__ RowRuns row_runs(const Grid &g, const QueryCell &c, i
     }
     xlo = max(xlo, 0); xhi = min(xhi, g.nx - 1);
     const size_t base = ((size_t)z * g.ny + y) * g.nx;
-    const uint32_t *row = g.cell_start + base;
     const bool probe = Rin >= 0;                     // first pass (whole block): the table rows are hot, read them directly
     if (max(abs(dz), abs(dy)) > Rin) {
-        if (xlo <= xhi && (!probe || row_occupied(g, base, xlo, xhi))) { r.j1 = __ldg(row + xlo); r.e1 = __ldg(row + xhi + 1); }
+        if (xlo <= xhi && (!probe || row_occupied(g, base, xlo, xhi))) { r.j1 = cell_begin(g, base + xlo); r.e1 = cell_begin(g, base + xhi + 1); }
     } else {
         const int xl = min(xhi, c.cx - Rin - 1);     // left strip [xlo, xl]
-        if (xlo <= xl && row_occupied(g, base, xlo, xl)) { r.j1 = __ldg(row + xlo); r.e1 = __ldg(row + xl + 1); }
+        if (xlo <= xl && row_occupied(g, base, xlo, xl)) { r.j1 = cell_begin(g, base + xlo); r.e1 = cell_begin(g, base + xl + 1); }
         const int xr = max(xlo, c.cx + Rin + 1);     // right strip [xr, xhi]
-        if (xr <= xhi && row_occupied(g, base, xr, xhi)) { r.j2 = __ldg(row + xr); r.e2 = __ldg(row + xhi + 1); }
+        if (xr <= xhi && row_occupied(g, base, xr, xhi)) { r.j2 = cell_begin(g, base + xr); r.e2 = cell_begin(g, base + xhi + 1); }
     }
     return r;
 }

@@ -64,6 +64,7 @@ struct pcc_index {
     pcc::Buf pts;             // float4 [n_indexed], sorted by cell
     pcc::Buf cell_start;      // uint32 [n_cells + 1]
     pcc::Buf occ;             // uint32 [n_cells / 32 + 2]: one bit per cell, set when the cell holds a point (derived from cell_start)
+    pcc::Buf occ2, cstart;    // compact cell table (pcc_device.cuh cell_begin): uint2 per 32 cells, uint32 per non-empty cell
     bool occ_valid = false;
     // scratch (grow-only, reused by every call on this index; calls on one index are serialised by the caller per stream)
     pcc::Buf raw, stage4, cellrank, qbuf, qkeys, qkeys2, qperm, qperm2, cub_tmp, out_i, out_f, out_l, keys64, keys64b, misc, parent, inv_pos, sel_params, icp_prior, calib;
@@ -98,7 +99,7 @@ struct pcc_index {
     pcc::Grid grid() const {
         const pcc_index *o = grid_owner ? grid_owner : this;
         pcc::Grid g;
-        g.pts = o->pts.as<float4>(); g.cell_start = o->cell_start.as<uint32_t>(); g.occ = o->occ.as<uint32_t>();
+        g.pts = o->pts.as<float4>(); g.cell_start = o->cell_start.as<uint32_t>(); g.occ = o->occ.as<uint32_t>(); g.occ2 = o->occ2.as<uint2>(); g.cstart = o->cstart.as<uint32_t>();
         g.ox = o->gh.ox; g.oy = o->gh.oy; g.oz = o->gh.oz; g.inv_cell = o->gh.inv_cell; g.cell = o->gh.cell;
         g.nx = o->gh.nx; g.ny = o->gh.ny; g.nz = o->gh.nz; g.n = (uint32_t)o->n_indexed;
         return g;

@@ -328,8 +328,8 @@ __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, 
             const int zz = c.cz + centre_out(r / 3), yy = c.cy + centre_out(r % 3);
             rs[r] = re[r] = 0;
             if (zz >= 0 && zz < g.nz && yy >= 0 && yy < g.ny) {
-                const uint32_t *rowp = g.cell_start + ((size_t)zz * g.ny + yy) * g.nx;
-                rs[r] = __ldg(rowp + xa); re[r] = __ldg(rowp + xb + 1);
+                const size_t rowb = ((size_t)zz * g.ny + yy) * g.nx;
+                rs[r] = cell_begin(g, rowb + xa); re[r] = cell_begin(g, rowb + xb + 1);
             }
         }
 #pragma unroll
