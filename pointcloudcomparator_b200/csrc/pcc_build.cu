@@ -59,6 +59,8 @@ __global__ void extract_kernel(const uint8_t *__restrict__ raw, int stride, cons
 }
 
 struct BinParams { float ox, oy, oz, inv; int nx, ny, nz; };
+constexpr int64_t kFillSamples = 1 << 17;                 // points sampled by blockfill_kernel
+constexpr double kFillSurface = 15.0, kFillVolume = 21.0;  // occupied cells per 3x3x3 block: at or below = surface target, at or above = volume target, linear between
 __device__ __forceinline__ uint32_t cell_of(const BinParams &b, float x, float y, float z) {
     int cx = grid_c(grid_u(x, b.ox, b.inv), b.nx), cy = grid_c(grid_u(y, b.oy, b.inv), b.ny), cz = grid_c(grid_u(z, b.oz, b.inv), b.nz);
     return (uint32_t)(((size_t)cz * b.ny + cy) * b.nx + cx);
@@ -72,6 +74,25 @@ __global__ void bin_kernel(const float4 *__restrict__ stage, int64_t m, BinParam
     uint32_t c = cell_of(b, p.x, p.y, p.z);
     uint32_t r = atomicAdd(counts + c, 1u);
     if (cellrank) cellrank[i] = make_uint2(c, r);
+}
+// How many of the 27 cells around a point's cell hold a point, summed over every `stride`-th staged point: ~27 for a cloud that fills
+// its volume, 9-13 for a surface.  `counts` is the per-cell histogram (before the scan).  out[0] += occupied neighbours, out[1] += samples.
+__global__ void blockfill_kernel(const float4 *__restrict__ stage, int64_t m, int64_t stride, BinParams b, const uint32_t *__restrict__ counts, unsigned long long *__restrict__ out) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * stride;
+    unsigned filled = 0, sample = 0;
+    if (i < m) {
+        const float4 p = stage[i];
+        if (p.w == p.w) {
+            const int cx = grid_c(grid_u(p.x, b.ox, b.inv), b.nx), cy = grid_c(grid_u(p.y, b.oy, b.inv), b.ny), cz = grid_c(grid_u(p.z, b.oz, b.inv), b.nz);
+            sample = 1;
+            for (int z = max(cz - 1, 0); z <= min(cz + 1, b.nz - 1); ++z)
+                for (int y = max(cy - 1, 0); y <= min(cy + 1, b.ny - 1); ++y)
+                    for (int x = max(cx - 1, 0); x <= min(cx + 1, b.nx - 1); ++x)
+                        filled += counts[((size_t)z * b.ny + y) * b.nx + x] > 0u ? 1u : 0u;
+        }
+    }
+    filled = __reduce_add_sync(0xffffffffu, filled); sample = __reduce_add_sync(0xffffffffu, sample);
+    if ((threadIdx.x & 31) == 0 && sample) { atomicAdd(out, (unsigned long long)filled); atomicAdd(out + 1, (unsigned long long)sample); }
 }
 __global__ void nonzero_kernel(const uint32_t *__restrict__ counts, int64_t n, unsigned long long *__restrict__ out) {
     unsigned local = 0;
@@ -167,15 +188,29 @@ __global__ void qprep_kernel(const uint8_t *__restrict__ raw, int stride, int64_
 
 static inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)std::max<int64_t>(1, (n + threads - 1) / threads); }
 
+// Target points per NON-EMPTY cell.  PCC_OCC overrides it (measurement knob).
+// Surface-like clouds, measured on B200 (10 M queries on a 10 M-point surface cloud, kNN ms at target 4 / 6 / 8 / 10 / 12): k = 4: 3.46 / 2.60 /
+// 2.21 / - / -, k = 8: 4.31 / 3.14 / 2.71 / 2.76 / -, k = 16: - / 4.89 / 4.13 / 4.17 / 4.15, k = 32 at 12 / 16 / 20: 9.47 / 9.52 /
+// 10.4; k = 1 (own kernel) at 3 / 4 / 8: 2.68 / 2.36 / 1.80.  With ~8 points per occupied cell the 3x3x3 block settles >80 % of the queries for k <= 16; smaller cells send too
+// many of them to the ring passes, larger ones make the block walk longer.
 static double occupancy_target(int k_hint) {
-    const char *e = getenv("PCC_OCC");
-    if (e && atof(e) > 0) return atof(e);
     int k = k_hint > 0 ? k_hint : 16;
-    // Measured on B200 (10 M queries on a 10 M-point surface cloud, kNN ms at target 4 / 6 / 8 / 10 / 12): k = 4: 3.46 / 2.60 /
-    // 2.21 / - / -, k = 8: 4.31 / 3.14 / 2.71 / 2.76 / -, k = 16: - / 4.89 / 4.13 / 4.17 / 4.15, k = 32 at 12 / 16 / 20: 9.47 / 9.52 /
-    // 10.4; k = 1 (own kernel) at 3 / 4 / 8: 2.68 / 2.36 / 1.80.  With ~8 points per occupied cell the 3x3x3 block settles >80 % of the queries for k <= 16; smaller cells send too
-    // many of them to the ring passes, larger ones make the block walk longer.
     return std::max(8.0, 0.5 * k);
+}
+// Volume-filling clouds: all 27 cells of a block are occupied (a surface fills 9-13), so the same block population needs
+// a third of the points per cell.  Measured on a 10 M-point uniform cube, 10 M queries (profiles/r2/occupancy_uniform_cloud.txt), best
+// target / kNN ms there vs ms at 8 per cell: k = 1: 1.3-1.9 / 0.99 vs 1.37; k = 2: 1.9 / 1.58 vs 2.16; k = 4: 1.9 / 1.66 vs 2.31 (1.3: 2.50);
+// k = 8: 2.3-3.1 / 2.32 vs 3.02; k = 16: 4 / 3.63 vs 4.48; k = 32: 5-6 / 11.2 vs 12.4 (16, the surface target: 15.7; 3: 24.0).
+// k > 32 (selection path) is flat in the target (k = 50: 20.4 ms at 4 and at 25).
+static double occupancy_target_volume(int k_hint) {
+    int k = k_hint > 0 ? k_hint : 16;
+    if (k > 32) return 0.5 * k;
+    return std::max(1.9, std::min(k / 3.5, 4.0 + (k - 16) / 10.0));
+}
+static bool occupancy_override(double *v) {
+    const char *e = getenv("PCC_OCC");
+    if (e && atof(e) > 0) { *v = atof(e); return true; }
+    return false;
 }
 
 static void dims_for(const double ext[3], double cell, int dims[3]) {
@@ -380,7 +415,8 @@ int pcc_build(pcc_index *idx, const void *pts, int64_t n, int stride_bytes, cons
     const double mx = std::max(ext[0], std::max(ext[1], ext[2]));
     double cell;
     const bool autotune = !(cell_hint > 0);
-    const double target = occupancy_target(k_hint);
+    double target = occupancy_target(k_hint);
+    const bool target_fixed = occupancy_override(&target);
     if (!autotune) cell = cell_hint;
     else {
         int live = 0; double vol = 1;
@@ -392,7 +428,7 @@ int pcc_build(pcc_index *idx, const void *pts, int64_t n, int stride_bytes, cons
     PCC_TRY(idx->cellrank.reserve((size_t)m * sizeof(uint2)));
     BinParams b{};
     int dims[3]; int64_t n_cells = 0; double occ = 0;
-    double prev_cell = 0, prev_occ = 0;
+    double prev_cell = 0, prev_occ = 0, dim_first = 2.0;
     for (int it = 0; it < 5; ++it) {
         dims_for(ext, cell, dims);
         n_cells = (int64_t)dims[0] * dims[1] * dims[2];
@@ -400,19 +436,33 @@ int pcc_build(pcc_index *idx, const void *pts, int64_t n, int stride_bytes, cons
         b = BinParams{(float)lo[0], (float)lo[1], (float)lo[2], 1.0f / cellf, dims[0], dims[1], dims[2]};
         PCC_TRY(idx->cell_start.reserve((size_t)(n_cells + 1) * sizeof(uint32_t)));
         PCC_CUDA(cudaMemsetAsync(idx->cell_start.p, 0, (size_t)(n_cells + 1) * sizeof(uint32_t), s));
-        PCC_CUDA(cudaMemsetAsync(d_scal + 10, 0, 8, s));
+        PCC_CUDA(cudaMemsetAsync(d_scal + 10, 0, 24, s));
         bin_kernel<<<blocks_for(m, 256), 256, 0, s>>>(idx->stage4.as<float4>(), m, b, idx->cell_start.as<uint32_t>(), idx->cellrank.as<uint2>());
         PCC_LAUNCHED();
         nonzero_kernel<<<(unsigned)std::min<int64_t>(blocks_for(n_cells, 256), 148 * 16), 256, 0, s>>>(idx->cell_start.as<uint32_t>(), n_cells, (unsigned long long *)(d_scal + 10));
         PCC_LAUNCHED();
+        const bool probe_fill = autotune && !target_fixed && it == 0;     // surface or volume?  decided once, on the first grid
+        if (probe_fill) {
+            const int64_t stride = std::max<int64_t>(1, m / kFillSamples);
+            blockfill_kernel<<<blocks_for((m + stride - 1) / stride, 256), 256, 0, s>>>(idx->stage4.as<float4>(), m, stride, b, idx->cell_start.as<uint32_t>(), (unsigned long long *)(d_scal + 12));
+            PCC_LAUNCHED();
+        }
         PCC_CUDA(cudaGetLastError());
-        PCC_CUDA(cudaMemcpyAsync(h + 10, d_scal + 10, 8, cudaMemcpyDeviceToHost, s));
+        PCC_CUDA(cudaMemcpyAsync(h + 10, d_scal + 10, 24, cudaMemcpyDeviceToHost, s));
         PCC_CUDA(cudaStreamSynchronize(s));
         const int64_t nonempty = (int64_t)(*(unsigned long long *)(h + 10));
         occ = (double)nfin / (double)std::max<int64_t>(nonempty, 1);
+        if (probe_fill) {
+            const unsigned long long filled = *(unsigned long long *)(h + 12), samples = *(unsigned long long *)(h + 14);
+            const double nb = samples ? (double)filled / (double)samples : 0.0;      // occupied cells of a 3x3x3 block, mean over the sample
+            const double w = std::min(1.0, std::max(0.0, (nb - kFillSurface) / (kFillVolume - kFillSurface)));
+            target = (1.0 - w) * target + w * occupancy_target_volume(k_hint);
+            dim_first = 2.0 + w;
+            idx->gh.block_fill = nb;
+        }
         if (!autotune || it == 4) break;
-        if (occ > 0.75 * target && occ < 1.4 * target) break;
-        double dim_est = 2.0;   // first correction assumes a surface; afterwards use the measured scaling exponent
+        if (occ > 0.9 * target && occ < 1.4 * target) break;      // the cost curve is steep below the target (ring passes), shallow above it
+        double dim_est = dim_first;   // first correction: 2 for a surface, 3 for a filled volume; afterwards the measured scaling exponent
         if (prev_cell > 0 && prev_occ > 0 && std::fabs(std::log(cell / prev_cell)) > 1e-3) {
             dim_est = std::log(occ / prev_occ) / std::log(cell / prev_cell);
             dim_est = std::min(3.0, std::max(1.0, dim_est));

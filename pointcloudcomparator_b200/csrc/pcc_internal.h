@@ -49,6 +49,7 @@ struct GridHost {
     float ox = 0, oy = 0, oz = 0, cell = 1, inv_cell = 1;
     int nx = 1, ny = 1, nz = 1;
     double occupancy = 0;      // mean points per non-empty cell
+    double block_fill = 0;     // occupied cells per 3x3x3 block around a point, measured on the first auto-tune grid (0 = not measured)
     int64_t n_cells = 1;
 };
 

@@ -70,6 +70,18 @@ def test_knn_uniform_volume_and_mismatched_k_hint(GS):
         assert_knn_equal(gi, gd, oi, od)
 
 
+def test_grid_autotune_tells_surface_from_volume(GS):
+    """The cell size is chosen from the measured cloud: ~8 points per occupied cell on a surface (9-13 of the 27 cells of a block are
+    occupied), about half of that in a filled volume (all 27 are) -- csrc/pcc_build.cu occupancy_target / occupancy_target_volume.
+    Results stay exact either way (every kNN test); this pins the choice itself."""
+    vol = GS().setInputCloud(synth.uniform(300000, 5001, extent=4.0), k_hint=16).grid_info()["occupancy"]
+    surf = GS().setInputCloud(synth.room(300000, 4001, size=(10.0, 10.0, 3.0)), k_hint=16).grid_info()["occupancy"]
+    assert 3.5 <= vol <= 5.7, vol
+    assert 7.0 <= surf <= 11.5, surf
+    vol4 = GS().setInputCloud(synth.uniform(300000, 5001, extent=4.0), k_hint=4).grid_info()["occupancy"]
+    assert 1.7 <= vol4 <= 2.7, vol4
+
+
 def test_knn_lattice_ties_everywhere(GS):
     g = np.arange(16, dtype=np.float32) * 0.25
     ref = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
