@@ -195,6 +195,7 @@ static inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)std
 // many of them to the ring passes, larger ones make the block walk longer.
 static double occupancy_target(int k_hint) {
     int k = k_hint > 0 ? k_hint : 16;
+    if (k == 1) return 12.0;       // k = 1 at 8 / 10 / 12 / 16 / 20: 1.79 / 1.74 / 1.62 / 1.64 / 1.70 ms (k = 2, 4, 8 are best at 8; profiles/r2/occupancy_surface_small_k.txt)
     return std::max(8.0, 0.5 * k);
 }
 // Volume-filling clouds: all 27 cells of a block are occupied (a surface fills 9-13), so the same block population needs
