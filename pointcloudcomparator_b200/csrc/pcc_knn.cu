@@ -884,7 +884,8 @@ static int calibrate_thr(pcc_index *idx, const Grid &g, const QueryView &v, int 
     const int64_t stride = std::max<int64_t>(1, v.nq / kCalibSample), ns = (v.nq + stride - 1) / stride;
     knn_calib_kernel<K><<<nblocks(ns, 128), 128, 0, s>>>(g, v, k, stride, hist);
     PCC_LAUNCHED();
-    knn_calib_finish_kernel<<<1, kCalibBuckets, 0, s>>>(hist, ratio, kCalibQuantile);
+    static const float quantile = getenv("PCC_THR_QUANTILE") ? (float)atof(getenv("PCC_THR_QUANTILE")) : kCalibQuantile;      // measurement knob
+    knn_calib_finish_kernel<<<1, kCalibBuckets, 0, s>>>(hist, ratio, quantile);
     PCC_LAUNCHED();
     return PCC_OK;
 }
