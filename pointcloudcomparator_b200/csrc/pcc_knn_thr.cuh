@@ -32,6 +32,12 @@
 
 namespace pcc {
 
+#ifndef PCC_THR_EARLY
+#define PCC_THR_EARLY 16
+#endif
+#ifndef PCC_THR_JOINT
+#define PCC_THR_JOINT 1
+#endif
 #ifndef PCC_THR_SLOTS8
 #define PCC_THR_SLOTS8 36
 #endif
@@ -210,7 +216,7 @@ __device__ __forceinline__ void thr_quad(const Quad &q, const uint32_t j, const 
     sts_v2(wa, __float_as_uint(d3), j + 3); advance_if_le<STRIDE>(wa, d3, tau);
     dmin = fminf(fminf(dmin, fminf(d0, d1)), fminf(d2, d3)); tau = dmin + T;
     if (!COMPRESS) wa = min(wa, cap);
-    else if (wa >= cap) on_full();                        // not clamped first: the entries in the sacrificial slots are real
+    else if (PCC_THR_JOINT ? __any_sync(__activemask(), wa >= cap) : (wa >= cap)) on_full();      // not clamped first: the entries in the sacrificial slots are real
 }
 // PCC_THR_PIPE = 1 software-pipelines the walk (the four loads of step i+1 are issued before step i is processed, two register
 // sets, loop unrolled by two).  Measured on B200: no gain (3.62 vs 3.51 ms for the stage, and the retry kernel doubles) -- the
@@ -253,7 +259,7 @@ __device__ __forceinline__ void thr_walk_run(const float4 *pts, uint32_t j, cons
         sts_v2(wa, __float_as_uint(d2), j + 2); advance_if_le_and<STRIDE>(wa, d2, tau, j + 2 < e);
         dmin = fminf(fminf(dmin, d0), fminf(d1, d2)); tau = dmin + T;
         if (!COMPRESS) wa = min(wa, cap);
-        else if (wa >= cap) on_full();                    // not clamped first: the entries in the sacrificial slots are real
+        else if (PCC_THR_JOINT ? __any_sync(__activemask(), wa >= cap) : (wa >= cap)) on_full();      // not clamped first: the entries in the sacrificial slots are real
     }
 }
 
@@ -415,8 +421,9 @@ __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, 
         return kth;
     };
     bool give_up = false;
-    auto on_full = [&]() {                                // RETRY only: compress the full log in place (see above)
-        const int nf = (int)((wa - wa0) / STRIDE);        // LOGCAP .. LOGCAP + 3 entries
+    auto compress_if = [&](const int min_n) {             // RETRY only: compress the log in place (see above) if it holds >= min_n entries
+        const int nf = (int)((wa - wa0) / STRIDE);        // LOGCAP .. LOGCAP + 3 entries when the log is full
+        if (nf < min_n) return;
         select_log(nf);
         const float tau_new = __uint_as_float(slog[(kth_key() & SMASK) * TH].x) * (1.f + 1.f / 32768.f);     // 2^-15 covers the key truncation
         // The log is complete up to the CURRENT tau only (earlier entries passed looser thresholds), so tau may shrink to tau_new
@@ -427,6 +434,9 @@ __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, 
         if (m >= LOGCAP - 4) { give_up = true; m = 0; }   // more candidates inside tau than the log holds (ties)
         wa = wa0 + (uint32_t)m * STRIDE;
     };
+    // called when SOME lane of the warp is full (PCC_THR_JOINT): that lane must compress, the others join it if they have a
+    // worthwhile number of entries to drop, so that they do not stop the warp again a few steps later
+    auto on_full = [&]() { compress_if(wa >= cap ? 0 : K + 13); };
     // the walk: rows centre-out, each clipped to the ball of the current tau (bounds of row i+1 fetched before row i is walked)
     {
         const RowRuns none = {0u, 0u, 0u, 0u};
@@ -449,6 +459,14 @@ __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, 
             } else thr_walk_run<STRIDE, COMPRESS, false>(g.pts, cur.j1, cur.e1, x, y, z, T, dmin, tau, wa, cap, on_full);
             (void)r;
             if (!more) break;
+            if (COMPRESS && PCC_THR_EARLY > 0) {
+                // Compress together.  A lane whose log fills inside a row compresses alone while the other 31 wait for its ~800
+                // instructions (ncu, retry pass: 6 of 32 lanes active, half of the samples in compression code).  So at a row
+                // boundary, once any lane is within PCC_THR_EARLY slots of full, every lane that has entries to drop compresses in
+                // the same pass (legal at any time with >= k entries: tau only shrinks).
+                const int nl = (int)((wa - wa0) / STRIDE);
+                if (__any_sync(__activemask(), nl >= LOGCAP - PCC_THR_EARLY)) compress_if(K + 5);
+            }
         }
     }
     if (STAGED && !live) { leave_dead(); return; }
