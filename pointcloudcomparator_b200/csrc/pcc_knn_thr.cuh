@@ -32,6 +32,9 @@
 
 namespace pcc {
 
+#ifndef PCC_THR_QAHEAD
+#define PCC_THR_QAHEAD 0          // blocks of look-ahead for the query prefetch (0 = off)
+#endif
 #ifndef PCC_THR_EARLY
 #define PCC_THR_EARLY 16
 #endif
@@ -313,6 +316,16 @@ __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, 
     constexpr uint32_t SMASK = (1u << ThrCfg<K>::slot_bits) - 1u;
     const int k = FULLK ? K : k_rt;
     float x = 0.f, y = 0.f, z = 0.f; int64_t row = 0; bool empty = false;
+#if PCC_THR_QAHEAD
+    // A block starts with two dependent cache misses (order[t], then the query it names) before it has anything to do: 8 % of the kernel's
+    // stall samples.  Blocks run in launch order, so this block asks L2 for what the blocks ~one and ~two GPU-fulls later will read first.
+    uint32_t qi_ahead = 0xFFFFFFFFu;
+    if (!RETRY && !STAGED && v.order) {
+        constexpr int64_t AHEAD = (int64_t)PCC_THR_QAHEAD * ThrCfg<K>::threads;
+        if ((threadIdx.x & 31) == 0 && t + 2 * AHEAD < v.nq) prefetch_l2(v.order + t + 2 * AHEAD);
+        if (t + AHEAD < v.nq) qi_ahead = __ldg(v.order + t + AHEAD);
+    }
+#endif
     const bool live = load_query(g, v, t, x, y, z, row, empty);
     auto leave_dead = [&]() {                             // tail thread or non-finite query
         if (t < v.nq) fix.ring_flag[t] = 0;
@@ -342,6 +355,9 @@ __device__ __forceinline__ void knn_thr_body(const Grid &g, const QueryView &v, 
         for (int r = 0; r < 9; ++r) { M += re[r] - rs[r]; rowmask |= (re[r] > rs[r] ? 1u : 0u) << r; if (!STAGED && (PCC_THR_PREFETCH & 1)) prefetch_run<3, false>(g.pts, rs[r], re[r]); }
         s0 = rs[0]; e0 = re[0];
     }
+#if PCC_THR_QAHEAD
+    if (!RETRY && !STAGED && qi_ahead != 0xFFFFFFFFu) prefetch_l2(v.q + qi_ahead);
+#endif
     auto leave_wide = [&]() {                             // fewer than k points in the block: a wide query (no walk)
         fix.ring_flag[t] = 0;
         if (fix.stats) { atomicAdd(fix.stats + 0, 1ull); atomicAdd(fix.stats + 4, 1ull); }
