@@ -417,5 +417,51 @@ class RegionGrowing {
     float theta_ = 30.0f / 180.0f * 3.14159265358979f, curvature_ = 0.05f;
 };
 
+// pcl::RegionGrowingRGB<PointT>::extract as color_growing_segmentation uses it (src/segmentation.cpp:179-190: distance 10, point colour 6,
+// region colour 5, min cluster 200; neither the search k nor the neighbour number is set, so the table has PCL's 100 columns and the
+// grow phase walks the first 30).  The N x 100 table + squared distances come from one batched GPU query; grow / merge / fold of small
+// regions run on the host over it (pcc_region_growing_rgb).  PointT must carry PCL's packed colour word at `rgba_offset` bytes
+// (16 for pcl::PointXYZRGB and for the stand-in above).
+template <typename PointT>
+class RegionGrowingRGB {
+  public:
+    explicit RegionGrowingRGB(int rgba_offset = 16) : rgba_off_(rgba_offset) {}
+    void setSearchMethod(const typename search::GridSearch<PointT>::Ptr &tree) { tree_ = tree; }
+    void setInputCloud(const typename search::GridSearch<PointT>::PointCloudConstPtr &cloud) { input_ = cloud; }
+    void setDistanceThreshold(float d) { distance_ = d; }
+    void setPointColorThreshold(float t) { point_color_ = t; }
+    void setRegionColorThreshold(float t) { region_color_ = t; }
+    void setNumberOfRegionNeighbours(unsigned int k) { table_k_ = (int)k; }       // RegionGrowingRGB::region_neighbour_number_ (the table's width)
+    void setNumberOfNeighbours(unsigned int k) { grow_k_ = (int)k; }              // RegionGrowing::neighbour_number_ (what growRegion walks)
+    void setMinClusterSize(int n) { min_size_ = n; }
+    void setMaxClusterSize(int n) { max_size_ = n; }
+    void extract(std::vector<PointIndices> &clusters) {
+        clusters.clear();
+        if (!input_) throw Error("RegionGrowingRGB: no input cloud");
+        const size_t n = input_->points.size();
+        if (n == 0) return;
+        if (!tree_) tree_.reset(new search::GridSearch<PointT>());
+        tree_->setKHint(table_k_);
+        if (tree_->getInputCloud() != input_) tree_->setInputCloud(input_);
+        std::vector<int> nbrs; std::vector<float> d2;
+        const int k = findPointNeighbours(*tree_, table_k_, nbrs, d2);
+        labels_.assign(n, -1);
+        int64_t nc = 0;
+        const uint32_t *rgba = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(input_->points.data()) + rgba_off_);
+        check(pcc_region_growing_rgb(nbrs.data(), d2.data(), (int64_t)n, k, rgba, (int)sizeof(PointT), distance_, point_color_, region_color_,
+                                     std::min(grow_k_, k), min_size_, max_size_, labels_.data(), &nc));
+        clusters.resize((size_t)nc);
+        for (size_t i = 0; i < n; ++i) if (labels_[i] >= 0) clusters[(size_t)labels_[i]].indices.push_back((int)i);
+    }
+    const std::vector<int32_t> &labels() const { return labels_; }
+  private:
+    typename search::GridSearch<PointT>::Ptr tree_;
+    typename search::GridSearch<PointT>::PointCloudConstPtr input_;
+    std::vector<int32_t> labels_;
+    int rgba_off_, table_k_ = 100, grow_k_ = 30;
+    int64_t min_size_ = 1, max_size_ = std::numeric_limits<int>::max();
+    float distance_ = 10.f, point_color_ = 1225.f, region_color_ = 10.f;          // PCL 1.7 constructor defaults
+};
+
 }  // namespace pcc
 #endif  // PCC_GRID_SEARCH_HPP_

@@ -139,6 +139,26 @@ int main() {
         for (size_t j = 0; j < regions[c].indices.size(); ++j) { REQUIRE(!seen[(size_t)regions[c].indices[j]]); seen[(size_t)regions[c].indices[j]] = 1; }
     }
 
-    std::printf("PASS grid_search host mirror: kNN/radius/indices/normals/SOR/ECE/ICP/VoxelGrid/neighbour-table/RegionGrowing (%lld kernel launches)\n", (long long)pcc_launch_count());
+    // RegionGrowingRGB with the reference's settings (src/segmentation.cpp:179-190) on a slab painted in two colours: two clusters, split
+    // exactly at the colour edge, each holding every point of its half
+    {
+        typedef pcc::PointXYZRGB C; typedef pcc::PointCloud<C> CCloud;
+        CCloud::Ptr slab(new CCloud);
+        for (int i = 0; i < 2400; ++i) { C p; p.x = frand() * 2.f; p.y = frand(); p.z = frand() * 0.01f; const bool left = p.x < 1.f; p.r = left ? 200 : 20; p.g = left ? 30 : 180; p.b = 40; p.a = 0; slab->push_back(p); }
+        pcc::search::GridSearch<C>::Ptr ctree(new pcc::search::GridSearch<C>());
+        pcc::RegionGrowingRGB<C> rgb; rgb.setInputCloud(slab); rgb.setSearchMethod(ctree);
+        rgb.setDistanceThreshold(10); rgb.setPointColorThreshold(6); rgb.setRegionColorThreshold(5); rgb.setMinClusterSize(200);
+        std::vector<pcc::PointIndices> segs; rgb.extract(segs);
+        REQUIRE(segs.size() == 2);
+        size_t total = 0;
+        for (size_t c = 0; c < segs.size(); ++c) {
+            total += segs[c].indices.size();
+            const bool left = (*slab)[(size_t)segs[c].indices[0]].x < 1.f;
+            for (size_t j = 0; j < segs[c].indices.size(); ++j) REQUIRE(((*slab)[(size_t)segs[c].indices[j]].x < 1.f) == left);
+        }
+        REQUIRE(total == slab->size());
+    }
+
+    std::printf("PASS grid_search host mirror: kNN/radius/indices/normals/SOR/ECE/ICP/VoxelGrid/neighbour-table/RegionGrowing/RegionGrowingRGB (%lld kernel launches)\n", (long long)pcc_launch_count());
     return 0;
 }
