@@ -463,5 +463,28 @@ class RegionGrowingRGB {
     float distance_ = 10.f, point_color_ = 1225.f, region_color_ = 10.f;          // PCL 1.7 constructor defaults
 };
 
+// matchRIFTFeaturesKnn (src/comparator.cpp:560-588): KdTreeFLANN<Histogram<32>> over descriptors1, nearestKSearch(k = 1) for every
+// descriptor of descriptors2, kept when the squared distance is < 0.05.  The returned vector starts with one 0, as the reference's
+// `std::vector<int> correspondence(1)` does (its callers use size()).  HistT is any POD whose first floats are the histogram
+// (pcl::Histogram<32>: 32 floats).  match_dims = 3 reproduces the reference binary, where PCL 1.7's DefaultPointRepresentation
+// clamps the unregistered Histogram<32> to its first three floats; match_dims = 32 matches on the whole histogram.
+template <typename HistT>
+inline std::vector<int> matchRIFTFeaturesKnn(const std::vector<HistT> &descriptors1, const std::vector<HistT> &descriptors2, int match_dims = 3,
+                                             float threshold = 0.05f, int device = 0) {
+    static_assert(sizeof(HistT) % sizeof(float) == 0, "descriptor rows must be whole floats");
+    std::vector<int> correspondence(1);
+    if (descriptors1.empty() || descriptors2.empty()) return correspondence;
+    pcc_index *ws = nullptr;
+    check(pcc_create(device, &ws));
+    std::vector<int32_t> idx(descriptors2.size()); std::vector<float> d2(descriptors2.size());
+    const int rc = pcc_descriptor_nn(ws, reinterpret_cast<const float *>(descriptors1.data()), (int64_t)descriptors1.size(),
+                                     reinterpret_cast<const float *>(descriptors2.data()), (int64_t)descriptors2.size(), match_dims,
+                                     (int)(sizeof(HistT) / sizeof(float)), idx.data(), d2.data(), PCC_HOST, nullptr);
+    pcc_destroy(ws);
+    check(rc);
+    for (size_t i = 0; i < idx.size(); ++i) if (idx[i] >= 0 && d2[i] < threshold) correspondence.push_back(idx[i]);
+    return correspondence;
+}
+
 }  // namespace pcc
 #endif  // PCC_GRID_SEARCH_HPP_

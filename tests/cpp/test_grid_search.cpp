@@ -159,6 +159,28 @@ int main() {
         REQUIRE(total == slab->size());
     }
 
-    std::printf("PASS grid_search host mirror: kNN/radius/indices/normals/SOR/ECE/ICP/VoxelGrid/neighbour-table/RegionGrowing/RegionGrowingRGB (%lld kernel launches)\n", (long long)pcc_launch_count());
+    // matchRIFTFeaturesKnn (src/comparator.cpp:560-588) against an in-test brute force, in the reference-exact 3-float mode and on all 32 bins
+    {
+        struct Hist32 { float histogram[32]; };
+        std::vector<Hist32> d1(300), d2v(200);
+        for (size_t i = 0; i < d1.size(); ++i) for (int b = 0; b < 32; ++b) d1[i].histogram[b] = frand() * 0.3f;
+        for (size_t i = 0; i < d2v.size(); ++i) { d2v[i] = d1[(i * 7) % d1.size()]; for (int b = 0; b < 32; ++b) d2v[i].histogram[b] += (i % 3 == 0 ? 0.2f : 0.002f) * (frand() - 0.5f); }
+        for (int dims = 3; dims <= 32; dims += 29) {
+            const std::vector<int> got = pcc::matchRIFTFeaturesKnn(d1, d2v, dims);
+            std::vector<int> want(1);
+            for (size_t i = 0; i < d2v.size(); ++i) {
+                int best = -1; float bd = 0.f;
+                for (size_t j = 0; j < d1.size(); ++j) {
+                    float s = 0.f;
+                    for (int b = 0; b < dims; ++b) { const float d = d2v[i].histogram[b] - d1[j].histogram[b]; s = s + d * d; }
+                    if (best < 0 || s < bd) { best = (int)j; bd = s; }
+                }
+                if (best >= 0 && bd < 0.05f) want.push_back(best);
+            }
+            REQUIRE(got == want && got.size() > 1 && got[0] == 0);
+        }
+    }
+
+    std::printf("PASS grid_search host mirror: kNN/radius/indices/normals/SOR/ECE/ICP/VoxelGrid/neighbour-table/RegionGrowing/RegionGrowingRGB/matchRIFTFeaturesKnn (%lld kernel launches)\n", (long long)pcc_launch_count());
     return 0;
 }
