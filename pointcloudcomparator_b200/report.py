@@ -41,8 +41,10 @@ def centroid_f32(points) -> list:
 
 
 def distance_centroids(c1, c2) -> np.float32:
-    """distanceCentroids (:1047-1054): pow(float, 2) promotes to double, the sum is stored in a float, sqrt of that float."""
-    d = np.float32((float(c1[0]) - float(c2[0])) ** 2 + (float(c1[1]) - float(c2[1])) ** 2 + (float(c1[2]) - float(c2[2])) ** 2)
+    """distanceCentroids (:1047-1054): the differences are float subtractions, pow(float, 2) promotes each to double, the sum is stored
+    in a float, sqrt of that float."""
+    dx, dy, dz = (float(np.float32(np.float32(a) - np.float32(b))) for a, b in zip(c1[:3], c2[:3]))
+    d = np.float32(dx ** 2 + dy ** 2 + dz ** 2)
     return np.float32(math.sqrt(float(d)))
 
 

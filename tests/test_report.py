@@ -92,3 +92,65 @@ def test_no_match_no_clusters_and_number_format():
     # every point removed is the only way to a non-zero noise figure
     t2, _ = report.write_results("A", "B", 100, 50, c1, [], [10], [], lambda i, j: 0, None, noise_kept=(0, 25))
     assert "\tPCL1 has more noisy points: (%) 100 over: (%) 0\n" in t2
+
+
+# ---- the C++ twin (include/pcc/report.hpp): identical text and return code on the same inputs ----------------------------------
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def report_exe(tmp_path_factory):
+    cxx = shutil.which("g++")
+    if not cxx:
+        pytest.skip("no g++")
+    exe = str(tmp_path_factory.mktemp("report") / "test_report")
+    subprocess.run([cxx, "-O1", "-std=c++17", "-ffp-contract=off", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_report.cpp")], check=True)
+    return exe
+
+
+def _run_cpp(exe, name1, name2, n1, n2, c1, c2, nd1, nd2, corr, colours, icp, noise_kept):
+    lines = [f"{name1} {name2} {n1} {n2} {-1 if icp is None else int(icp)} {0 if noise_kept is None else 1} "
+             f"{0 if noise_kept is None else noise_kept[0]} {0 if noise_kept is None else noise_kept[1]} {len(c1)} {len(c2)}"]
+    for c, nd in list(zip(c1, nd1)) + list(zip(c2, nd2)):
+        lines.append(f"{len(c)} {nd} " + " ".join("%.9g" % v for v in np.asarray(c, np.float32)[:, :3].ravel()))
+    lines.append(" ".join(str(corr(i, j)) for i in range(len(c1)) for j in range(len(c2))))
+    lines.append(" ".join("%d %d" % colours(i, j) for i in range(len(c1)) for j in range(len(c2))))
+    out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    head, _, text = out.stdout.partition("\n")
+    return text, int(head[3:])
+
+
+def test_cpp_report_writer_matches_python_twin(report_exe):
+    rng = np.random.default_rng(11)
+    cases = []
+    c1 = [_cluster((0, 0, 0), 1200, 1), _cluster((2, 0, 0), 800, 2)]
+    c2 = [_cluster((2.01, 0, 0), 900, 3), _cluster((0.01, 0, 0), 1500, 4), _cluster((9, 9, 9), 60, 5)]
+    corr = {(0, 1): 41, (1, 0): 30}
+    cases.append(("A.ply", "B.ply", 2100, 2500, c1, c2, [40, 30], [28, 40, 5], lambda i, j: corr.get((i, j), 1), lambda i, j: ((3, 5), (4, 4))[i], True, (2000, 2400)))
+    cases.append(("a", "b", 1000, 900, [], [], [], [], lambda i, j: 0, lambda i, j: (0, 0), False, None))
+    cases.append(("a", "b", 100, 0, [_cluster((0, 0, 0), 100, 1)], [], [10], [], lambda i, j: 0, lambda i, j: (0, 0), None, None))
+    cases.append(("a", "b", 100, 50, [_cluster((0, 0, 0), 100, 1)], [], [10], [], lambda i, j: 0, lambda i, j: (0, 0), None, (0, 25)))
+    for seed in range(6):                                     # random scenes: 1-6 clusters per cloud at shared centres, random counts on both sides
+        k1, k2 = int(rng.integers(1, 7)), int(rng.integers(1, 7))
+        centres = rng.uniform(-3, 3, (8, 3))
+        a = [_cluster(centres[i], int(rng.integers(300, 1500)), 100 + seed * 10 + i) for i in range(k1)]
+        b = [_cluster(centres[j] + rng.normal(0, 0.02, 3), int(rng.integers(300, 1500)), 200 + seed * 10 + j) for j in range(k2)]
+        nd1, nd2 = [int(v) for v in rng.integers(2, 60, k1)], [int(v) for v in rng.integers(2, 60, k2)]
+        cm = rng.integers(1, 80, (k1, k2)); col = rng.integers(1, 9, (k1, k2, 2))
+        na, nb = sum(len(x) for x in a) + 50, sum(len(x) for x in b) + 70
+        cases.append((f"s{seed}a", f"s{seed}b", na, nb, a, b, nd1, nd2, (lambda i, j, cm=cm: int(cm[i, j])), (lambda i, j, col=col: (int(col[i, j, 0]), int(col[i, j, 1]))),
+                      (None, True)[seed % 2], (None, (na - 7, nb))[seed % 3 == 0]))
+    matched = 0
+    for name1, name2, n1, n2, a, b, nd1, nd2, corr_fn, col_fn, icp, kept in cases:
+        want, want_rc = report.write_results(name1, name2, n1, n2, a, b, nd1, nd2, corr_fn, col_fn, icp=icp, noise_kept=kept)
+        got, got_rc = _run_cpp(report_exe, name1, name2, n1, n2, a, b, nd1, nd2, corr_fn, col_fn, icp, kept)
+        assert got == want and got_rc == want_rc, (name1, got[-400:], want[-400:])
+        matched += want.count("Matched cluster")
+    assert matched >= 4                                       # the random scenes do exercise the match lines
